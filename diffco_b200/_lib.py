@@ -1,0 +1,133 @@
+"""ctypes binding of libdiffco_b200.so — the C ABI declared in include/diffco_b200.h.
+
+The product path has no CPU fallback: if the shared object is missing the import of the native layer raises
+with the build command, and every compute entry point raises if CUDA is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdiffco_b200.so")
+
+DC_MAX_DOF = 16
+DC_MAX_LINKS = 16
+DC_MAX_KEYPOINTS = 16
+DC_MAX_ARMS = 2
+DC_MAX_ARM_JOINTS = 8
+DC_MAX_TOOL_POINTS = 2
+DC_MAX_FEATURES = 64
+DC_MAX_CLASSES = 8
+
+DC_F32, DC_F64 = 0, 1
+DC_FK_NONE, DC_FK_PLANAR_CHAIN, DC_FK_SE2_BODY, DC_FK_SE3_BODY, DC_FK_DH_ARMS, DC_FK_SE2_BASE_PLANAR_ARM = range(6)
+DC_K_RQ, DC_K_POLYHARMONIC, DC_K_MULTIQUADRIC = 1, 2, 3
+DC_GRAD_NONE, DC_GRAD_SUM, DC_GRAD_JAC = 0, 1, 2
+
+
+class DhArm(C.Structure):
+    _fields_ = [
+        ("n_joints", C.c_int32),
+        ("n_tool", C.c_int32),
+        ("joint_index", C.c_int32 * DC_MAX_ARM_JOINTS),
+        ("out_slot", C.c_int32 * DC_MAX_ARM_JOINTS),
+        ("tool_slot", C.c_int32 * DC_MAX_TOOL_POINTS),
+        ("a", C.c_double * DC_MAX_ARM_JOINTS),
+        ("d", C.c_double * DC_MAX_ARM_JOINTS),
+        ("s_alpha", C.c_double * DC_MAX_ARM_JOINTS),
+        ("c_alpha", C.c_double * DC_MAX_ARM_JOINTS),
+        ("theta0", C.c_double * DC_MAX_ARM_JOINTS),
+        ("base", C.c_double * 12),
+        ("offset", C.c_double * 3),
+        ("tool", (C.c_double * 3) * DC_MAX_TOOL_POINTS),
+    ]
+
+
+class FkDesc(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("dof", C.c_int32),
+        ("n_points", C.c_int32),
+        ("point_dim", C.c_int32),
+        ("n_arms", C.c_int32),
+        ("n_keypoints", C.c_int32),
+        ("n_links", C.c_int32),
+        ("reserved", C.c_int32),
+        ("link_length", C.c_double * DC_MAX_LINKS),
+        ("keypoints", (C.c_double * DC_MAX_KEYPOINTS) * 3),
+        ("arms", DhArm * DC_MAX_ARMS),
+    ]
+
+    @property
+    def n_features(self) -> int:
+        return self.dof if self.type == DC_FK_NONE else self.n_points * self.point_dim
+
+
+class KernelDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("order", C.c_int32), ("param", C.c_double)]
+
+
+class Supports(C.Structure):
+    _fields_ = [
+        ("table", C.c_void_p),
+        ("n", C.c_int64),
+        ("n_features", C.c_int32),
+        ("n_class", C.c_int32),
+        ("f_pad", C.c_int32),
+        ("row_stride", C.c_int32),
+        ("dtype", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); must list every function declared in include/diffco_b200.h
+PROTOTYPES = {
+    "dc_abi_version": (C.c_int, []),
+    "dc_status_string": (C.c_char_p, [C.c_int]),
+    "dc_launch_count": (C.c_int64, []),
+    "dc_supports_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dc_pack_supports": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_score_workspace_bytes": (C.c_int64, [C.POINTER(FkDesc), C.POINTER(Supports), C.c_int64, C.c_int32]),
+    "dc_score_grad": (C.c_int, [C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p, C.c_int64,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_kernel_matrix": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                   C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_fk_forward": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_perceptron_train": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_void_p, C.c_void_p]),
+    "dc_fk_vjp": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libdiffco_b200.so (once).  Raises NativeLibraryError with the build recipe if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m diffco_b200.build` (nvcc, sm_100a). "
+            "diffco_b200 has no CPU or PyTorch fallback for the collision-score path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI mismatch, let it propagate
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dc_abi_version() != 1:
+        raise NativeLibraryError(f"ABI version mismatch: library reports {lib.dc_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().dc_status_string(status).decode()
+        raise RuntimeError(f"{what} failed: {msg} (dc_status {status})")

@@ -1,0 +1,392 @@
+// extern "C" entry points of libdiffco_b200.so (see include/diffco_b200.h) and the small helper kernels
+// (support-table packing, kernel matrix, stand-alone FK / FK-VJP).
+#include <cstring>
+
+#include "dc_common.cuh"
+#include "dc_fk.cuh"
+#include "dc_radial.cuh"
+#include "dc_score_ls.cuh"  // LsArgs only; kernels are instantiated in dc_score_ls_f32.cu / _f64.cu
+#include "dc_score_tq.cuh"
+
+namespace dc {
+
+long long g_launch_count = 0;
+
+#define DC_TQ_DECL(name) int name(int fp, ScoreArgs<float>& a, int num_sms, cudaStream_t stream);
+DC_TQ_DECL(tq_rq2_c1_score)
+DC_TQ_DECL(tq_rq2_c1_grad)
+DC_TQ_DECL(tq_rq2_c4_score)
+DC_TQ_DECL(tq_rq2_c4_grad)
+DC_TQ_DECL(tq_rq2_c4_jac)
+DC_TQ_DECL(tq_ph1_c1_score)
+DC_TQ_DECL(tq_ph1_c1_grad)
+DC_TQ_DECL(tq_ph1_c4_score)
+DC_TQ_DECL(tq_ph1_c4_grad)
+DC_TQ_DECL(tq_ph1_c4_jac)
+DC_TQ_DECL(tq_mq_c1_score)
+DC_TQ_DECL(tq_mq_c1_grad)
+DC_TQ_DECL(tq_mq_c4_score)
+DC_TQ_DECL(tq_mq_c4_grad)
+DC_TQ_DECL(tq_mq_c4_jac)
+#undef DC_TQ_DECL
+
+int ls_launch_f32(LsArgs<float>& a, int num_sms, cudaStream_t stream);
+int ls_launch_f64(LsArgs<double>& a, int num_sms, cudaStream_t stream);
+static int ls_launch(LsArgs<float>& a, int num_sms, cudaStream_t stream) { return ls_launch_f32(a, num_sms, stream); }
+static int ls_launch(LsArgs<double>& a, int num_sms, cudaStream_t stream) { return ls_launch_f64(a, num_sms, stream); }
+
+typedef int (*tq_fn)(int, ScoreArgs<float>&, int, cudaStream_t);
+// [kind][cw4][mode]
+static tq_fn const kTqTable[3][2][3] = {
+    {{tq_rq2_c1_score, tq_rq2_c1_grad, nullptr}, {tq_rq2_c4_score, tq_rq2_c4_grad, tq_rq2_c4_jac}},
+    {{tq_ph1_c1_score, tq_ph1_c1_grad, nullptr}, {tq_ph1_c4_score, tq_ph1_c4_grad, tq_ph1_c4_jac}},
+    {{tq_mq_c1_score, tq_mq_c1_grad, nullptr}, {tq_mq_c4_score, tq_mq_c4_grad, tq_mq_c4_jac}},
+};
+
+static int device_sm_count(int* out) {
+  static int cached_dev = -1, cached_sms = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return DC_ERR_NO_DEVICE;
+  }
+  if (dev != cached_dev) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return DC_ERR_NO_DEVICE;
+    }
+    cached_dev = dev;
+    cached_sms = sms;
+  }
+  *out = cached_sms;
+  return DC_OK;
+}
+
+static int fk_n_features(const dc_fk_desc& fk) { return fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim; }
+
+static bool fk_valid(const dc_fk_desc& fk) {
+  if (fk.dof < 1) return false;
+  const int F = fk_n_features(fk);
+  if (F < 1 || F > DC_MAX_FEATURES) return false;
+  switch (fk.type) {
+    case DC_FK_NONE:
+      return true;
+    case DC_FK_PLANAR_CHAIN:
+      return fk.dof <= DC_MAX_DOF && fk.n_links == fk.dof && fk.n_links <= DC_MAX_LINKS && fk.point_dim == 2 &&
+             fk.n_points == fk.dof;
+    case DC_FK_SE2_BODY:
+      return fk.dof == 3 && fk.point_dim == 2 && fk.n_keypoints == fk.n_points && fk.n_keypoints <= DC_MAX_KEYPOINTS;
+    case DC_FK_SE3_BODY:
+      return fk.dof == 6 && fk.point_dim == 3 && fk.n_keypoints == fk.n_points && fk.n_keypoints <= DC_MAX_KEYPOINTS;
+    case DC_FK_SE2_BASE_PLANAR_ARM:
+      return fk.dof == 3 + fk.n_links && fk.dof <= DC_MAX_DOF && fk.point_dim == 2 &&
+             fk.n_points == fk.n_keypoints + fk.n_links && fk.n_keypoints <= DC_MAX_KEYPOINTS;
+    case DC_FK_DH_ARMS: {
+      if (fk.dof > DC_MAX_DOF || fk.point_dim != 3 || fk.n_arms < 1 || fk.n_arms > DC_MAX_ARMS) return false;
+      for (int a = 0; a < fk.n_arms; ++a) {
+        const dc_dh_arm& arm = fk.arms[a];
+        if (arm.n_joints < 1 || arm.n_joints > DC_MAX_ARM_JOINTS || arm.n_tool < 0 || arm.n_tool > DC_MAX_TOOL_POINTS)
+          return false;
+        for (int i = 0; i < arm.n_joints; ++i) {
+          if (arm.joint_index[i] < 0 || arm.joint_index[i] >= fk.dof) return false;
+          if (arm.out_slot[i] >= fk.n_points) return false;
+        }
+        for (int k = 0; k < arm.n_tool; ++k)
+          if (arm.tool_slot[k] < 0 || arm.tool_slot[k] >= fk.n_points) return false;
+      }
+      return true;
+    }
+    default:
+      return false;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// helper kernels
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_supports_kernel(const T* __restrict__ s, const T* __restrict__ w, long long n, int F, int C, int f_pad,
+                                     int row, T* __restrict__ table) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * row) return;
+  const long long r = idx / row;
+  const int e = (int)(idx - r * row);
+  T v = (T)0;
+  if (e < F)
+    v = -s[r * F + e];
+  else if (e >= f_pad && e < f_pad + C)
+    v = w[r * C + (e - f_pad)];
+  table[idx] = v;
+}
+
+// K[i,j] = k(|xa_i - xb_j|^2): one CTA per (row i, 128-column block); xa_i staged in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(128) kernel_matrix_kernel(RadialConsts<T> rc, const T* __restrict__ xa, long long na,
+                                                            const T* __restrict__ xb, long long nb, int F,
+                                                            T* __restrict__ out) {
+  __shared__ T xi[DC_MAX_FEATURES];
+  const long long i = blockIdx.y;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) xi[f] = xa[i * F + f];
+  __syncthreads();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nb) return;
+  const T* xj = xb + j * F;
+  T rho = (T)0;
+  for (int f = 0; f < F; ++f) {
+    const T d = xi[f] - xj[f];
+    rho = fma(d, d, rho);
+  }
+  T k, coef;
+  radial_eval<KR_GENERIC, T>(rc, rho, k, coef);
+  out[i * nb + j] = k * rc.score_scale;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) fk_forward_kernel(const __grid_constant__ dc_fk_desc fk, const T* __restrict__ q,
+                                                         long long batch, T* __restrict__ x) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int F = fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim;
+  if (fk.type == DC_FK_NONE) {
+    for (int f = 0; f < F; ++f) x[b * F + f] = q[b * F + f];
+    return;
+  }
+  T qv[DC_MAX_DOF];
+#pragma unroll
+  for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < fk.dof) ? q[b * fk.dof + i] : (T)0;
+  fk_forward<T>(fk, qv, x + b * F, 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) fk_vjp_kernel(const __grid_constant__ dc_fk_desc fk, const T* __restrict__ q,
+                                                     long long batch, const T* __restrict__ gx, T* __restrict__ gq) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int F = fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim;
+  if (fk.type == DC_FK_NONE) {
+    for (int f = 0; f < F; ++f) gq[b * F + f] = gx[b * F + f];
+    return;
+  }
+  T qv[DC_MAX_DOF], out[DC_MAX_DOF], xl[DC_MAX_FEATURES], gl[DC_MAX_FEATURES];
+#pragma unroll
+  for (int i = 0; i < DC_MAX_DOF; ++i) {
+    qv[i] = (i < fk.dof) ? q[b * fk.dof + i] : (T)0;
+    out[i] = (T)0;
+  }
+  for (int f = 0; f < F; ++f) gl[f] = gx[b * F + f];
+  fk_forward<T>(fk, qv, xl, 1);
+  fk_vjp<T>(fk, qv, xl, 1, gl, 1, out);
+  for (int i = 0; i < fk.dof; ++i) gq[b * fk.dof + i] = out[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// typed implementations
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+static int score_grad_generic(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
+                              int64_t batch, void* score, void* grad, const void* grad_out, int32_t grad_mode,
+                              int num_sms, cudaStream_t stream) {
+  LsArgs<T> a;
+  a.fk = *fk;
+  if (!make_radial_consts<T>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
+  a.table = static_cast<const T*>(sv->table);
+  a.q = static_cast<const T*>(q);
+  a.score = static_cast<T*>(score);
+  a.grad = static_cast<T*>(grad);
+  a.grad_out = static_cast<const T*>(grad_out);
+  a.batch = batch;
+  a.n_sv = (int)sv->n;
+  a.n_feat = sv->n_features;
+  a.n_class = sv->n_class;
+  a.n_in = fk->dof;
+  a.f_pad = sv->f_pad;
+  a.row_stride = sv->row_stride;
+  a.grad_mode = grad_mode;
+  a.wpq = 1;
+  return ls_launch(a, num_sms, stream);
+}
+
+static bool tq_fp_available(int fp) {
+  switch (fp) {
+    case 1: case 2: case 3: case 4: case 6: case 7: case 8: case 11: case 12:
+      return true;
+    default:
+      return false;
+  }
+}
+
+// Batches below this go to the lane-split kernel (too few 64-query tiles to occupy the SMs).
+static constexpr int64_t kTqMinBatch = 2048;
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" {
+
+int dc_abi_version(void) { return DC_ABI_VERSION; }
+
+const char* dc_status_string(int status) {
+  switch (status) {
+    case DC_OK: return "ok";
+    case DC_ERR_INVALID_ARG: return "invalid argument";
+    case DC_ERR_UNSUPPORTED: return "unsupported configuration";
+    case DC_ERR_CUDA: return "CUDA error";
+    case DC_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown status";
+  }
+}
+
+int64_t dc_launch_count(void) { return g_launch_count; }
+
+int dc_supports_layout(int32_t n_features, int32_t n_class, int32_t dtype, int32_t* f_pad, int32_t* row_stride) {
+  if (n_features < 1 || n_features > DC_MAX_FEATURES || n_class < 1 || n_class > DC_MAX_CLASSES) return DC_ERR_INVALID_ARG;
+  if (dtype != DC_F32 && dtype != DC_F64) return DC_ERR_INVALID_ARG;
+  const int fp = 2 * ceil_div(n_features, 2);
+  if (f_pad) *f_pad = fp;
+  if (row_stride) *row_stride = round_up(fp + n_class, 4);
+  return DC_OK;
+}
+
+int dc_pack_supports(const void* s_feat, const void* w, int64_t n, int32_t n_features, int32_t n_class, int32_t dtype,
+                     void* table, dc_stream_t stream) {
+  int32_t f_pad = 0, row = 0;
+  const int st = dc_supports_layout(n_features, n_class, dtype, &f_pad, &row);
+  if (st != DC_OK) return st;
+  if (n < 1 || !s_feat || !w || !table) return DC_ERR_INVALID_ARG;
+  const long long total = (long long)n * row;
+  const int threads = 256;
+  const long long blocks = ceil_div64(total, threads);
+  if (dtype == DC_F32)
+    pack_supports_kernel<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        (const float*)s_feat, (const float*)w, n, n_features, n_class, f_pad, row, (float*)table);
+  else
+    pack_supports_kernel<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        (const double*)s_feat, (const double*)w, n, n_features, n_class, f_pad, row, (double*)table);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int64_t dc_score_workspace_bytes(const dc_fk_desc* fk, const dc_supports* sv, int64_t batch, int32_t grad_mode) {
+  (void)fk; (void)sv; (void)batch; (void)grad_mode;
+  return 0;
+}
+
+int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
+                  int64_t batch, void* score, void* grad, const void* grad_out, int32_t grad_mode, void* workspace,
+                  dc_stream_t stream) {
+  (void)workspace;
+  if (!fk || !kernel || !sv || !fk_valid(*fk)) return DC_ERR_INVALID_ARG;
+  if (batch == 0) return DC_OK;
+  if (batch < 0 || !q || !score || !sv->table || sv->n < 1 || sv->n > 0x7fffffff) return DC_ERR_INVALID_ARG;
+  if (grad_mode != DC_GRAD_NONE && grad_mode != DC_GRAD_SUM && grad_mode != DC_GRAD_JAC) return DC_ERR_INVALID_ARG;
+  if (grad_mode != DC_GRAD_NONE && !grad) return DC_ERR_INVALID_ARG;
+  const int F = fk_n_features(*fk);
+  int32_t f_pad = 0, row = 0;
+  if (dc_supports_layout(sv->n_features, sv->n_class, sv->dtype, &f_pad, &row) != DC_OK) return DC_ERR_INVALID_ARG;
+  if (F != sv->n_features || f_pad != sv->f_pad || row != sv->row_stride) return DC_ERR_INVALID_ARG;
+  int num_sms = 0;
+  const int st = device_sm_count(&num_sms);
+  if (st != DC_OK) return st;
+  cudaStream_t cs = (cudaStream_t)stream;
+
+  if (sv->dtype == DC_F64)
+    return score_grad_generic<double>(fk, kernel, sv, q, batch, score, grad, grad_out, grad_mode, num_sms, cs);
+
+  // fp32: thread-per-query kernel for large batches of the instantiated shapes, lane-split kernel otherwise
+  const int kind = fast_radial_kind(*kernel);
+  const int fp = f_pad / 2;
+  const int C = sv->n_class;
+  int mode = grad_mode == DC_GRAD_NONE ? M_SCORE : (grad_mode == DC_GRAD_SUM ? M_GRAD : M_JAC);
+  if (C == 1 && mode == M_JAC) mode = M_GRAD;  // one class: the Jacobian is the unit-upstream gradient
+  const void* go = (grad_mode == DC_GRAD_JAC) ? nullptr : grad_out;
+  if (kind != KR_GENERIC && C <= 4 && tq_fp_available(fp) && batch >= kTqMinBatch) {
+    tq_fn fn = kTqTable[kind][C == 1 ? 0 : 1][mode];
+    if (fn) {
+      ScoreArgs<float> a;
+      a.fk = *fk;
+      if (!make_radial_consts<float>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
+      a.table = (const float*)sv->table;
+      a.q = (const float*)q;
+      a.score = (float*)score;
+      a.grad = (float*)grad;
+      a.grad_out = (const float*)go;
+      a.batch = batch;
+      a.n_sv = (int)sv->n;
+      a.n_feat = F;
+      a.n_class = C;
+      a.n_in = fk->dof;
+      a.n_tiles = 0;
+      a.st_q = 0;
+      a.chunk_rows = 0;
+      const int r = fn(fp, a, num_sms, cs);
+      if (r != DC_ERR_UNSUPPORTED) return r;
+    }
+  }
+  return score_grad_generic<float>(fk, kernel, sv, q, batch, score, grad, grad_out, grad_mode, num_sms, cs);
+}
+
+int dc_kernel_matrix(const dc_kernel_desc* kernel, const void* xa, int64_t na, const void* xb, int64_t nb,
+                     int32_t n_features, int32_t dtype, void* k_out, dc_stream_t stream) {
+  if (!kernel || n_features < 1 || n_features > DC_MAX_FEATURES) return DC_ERR_INVALID_ARG;
+  if (na == 0 || nb == 0) return DC_OK;
+  if (na < 0 || nb < 0 || !xa || !xb || !k_out || na > 65535LL * 65535LL) return DC_ERR_INVALID_ARG;
+  cudaStream_t cs = (cudaStream_t)stream;
+  const long long bx = ceil_div64(nb, 128);
+  // gridDim.y is limited to 65535: walk the rows in slabs
+  for (long long i0 = 0; i0 < na; i0 += 65535) {
+    const long long rows = (na - i0 < 65535) ? (na - i0) : 65535;
+    dim3 grid((unsigned)bx, (unsigned)rows);
+    if (dtype == DC_F32) {
+      RadialConsts<float> rc;
+      if (!make_radial_consts<float>(*kernel, &rc)) return DC_ERR_INVALID_ARG;
+      kernel_matrix_kernel<float><<<grid, 128, 0, cs>>>(rc, (const float*)xa + i0 * n_features, rows, (const float*)xb, nb,
+                                                       n_features, (float*)k_out + i0 * nb);
+    } else if (dtype == DC_F64) {
+      RadialConsts<double> rc;
+      if (!make_radial_consts<double>(*kernel, &rc)) return DC_ERR_INVALID_ARG;
+      kernel_matrix_kernel<double><<<grid, 128, 0, cs>>>(rc, (const double*)xa + i0 * n_features, rows, (const double*)xb,
+                                                        nb, n_features, (double*)k_out + i0 * nb);
+    } else {
+      return DC_ERR_INVALID_ARG;
+    }
+    DC_LAUNCH_CHECK();
+  }
+  return DC_OK;
+}
+
+int dc_fk_forward(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, void* x_out, dc_stream_t stream) {
+  if (!fk || !fk_valid(*fk)) return DC_ERR_INVALID_ARG;
+  if (batch == 0) return DC_OK;
+  if (batch < 0 || !q || !x_out) return DC_ERR_INVALID_ARG;
+  const long long blocks = ceil_div64(batch, 128);
+  if (dtype == DC_F32)
+    fk_forward_kernel<float><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*fk, (const float*)q, batch, (float*)x_out);
+  else if (dtype == DC_F64)
+    fk_forward_kernel<double><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*fk, (const double*)q, batch, (double*)x_out);
+  else
+    return DC_ERR_INVALID_ARG;
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int dc_fk_vjp(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, const void* g_x, void* g_q,
+              dc_stream_t stream) {
+  if (!fk || !fk_valid(*fk)) return DC_ERR_INVALID_ARG;
+  if (batch == 0) return DC_OK;
+  if (batch < 0 || !q || !g_x || !g_q) return DC_ERR_INVALID_ARG;
+  const long long blocks = ceil_div64(batch, 128);
+  if (dtype == DC_F32)
+    fk_vjp_kernel<float><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*fk, (const float*)q, batch, (const float*)g_x,
+                                                                            (float*)g_q);
+  else if (dtype == DC_F64)
+    fk_vjp_kernel<double><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*fk, (const double*)q, batch,
+                                                                             (const double*)g_x, (double*)g_q);
+  else
+    return DC_ERR_INVALID_ARG;
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+}  // extern "C"

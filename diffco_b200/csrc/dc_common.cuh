@@ -1,0 +1,140 @@
+// Shared device/host helpers for the diffco_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/diffco_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "diffco_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace dc {
+
+extern long long g_launch_count;  // host-side counter, bumped by every launch wrapper (dc_launch_count()).
+
+#define DC_CUDA_OK(expr)                         \
+  do {                                           \
+    cudaError_t _e = (expr);                     \
+    if (_e != cudaSuccess) return DC_ERR_CUDA;   \
+  } while (0)
+
+#define DC_LAUNCH_CHECK()                        \
+  do {                                           \
+    ++dc::g_launch_count;                        \
+    if (cudaPeekAtLastError() != cudaSuccess) {  \
+      (void)cudaGetLastError();                  \
+      return DC_ERR_CUDA;                        \
+    }                                            \
+  } while (0)
+
+constexpr int kWarp = 32;
+
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ constexpr int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ constexpr int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// ----------------------------------------------------------------------------------------------
+// Packed pairs.  fp32 pairs map onto Blackwell's 2-wide FP32 instructions (FADD2/FMUL2/FFMA2 in SASS,
+// add/mul/fma.f32x2 in PTX): one issue slot, two lanes of work.  fp64 pairs are two scalars.
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+struct Pair;
+
+template <>
+struct Pair<float> {
+  float2 v;
+  __device__ __forceinline__ Pair() {}
+  __device__ __forceinline__ Pair(float a, float b) : v(make_float2(a, b)) {}
+  __device__ __forceinline__ explicit Pair(float2 f) : v(f) {}
+  __device__ __forceinline__ float lo() const { return v.x; }
+  __device__ __forceinline__ float hi() const { return v.y; }
+};
+
+template <>
+struct Pair<double> {
+  double a, b;
+  __device__ __forceinline__ Pair() {}
+  __device__ __forceinline__ Pair(double x, double y) : a(x), b(y) {}
+  __device__ __forceinline__ double lo() const { return a; }
+  __device__ __forceinline__ double hi() const { return b; }
+};
+
+__device__ __forceinline__ Pair<float> padd(Pair<float> x, Pair<float> y) { return Pair<float>(__fadd2_rn(x.v, y.v)); }
+__device__ __forceinline__ Pair<float> pfma(Pair<float> x, Pair<float> y, Pair<float> z) {
+  return Pair<float>(__ffma2_rn(x.v, y.v, z.v));
+}
+__device__ __forceinline__ Pair<double> padd(Pair<double> x, Pair<double> y) { return Pair<double>(x.a + y.a, x.b + y.b); }
+__device__ __forceinline__ Pair<double> pfma(Pair<double> x, Pair<double> y, Pair<double> z) {
+  return Pair<double>(fma(x.a, y.a, z.a), fma(x.b, y.b, z.b));
+}
+
+// ----------------------------------------------------------------------------------------------
+// Scalar math with the precision each dtype needs.  fp32: MUFU.RCP / MUFU.RSQ approximations
+// (<= 2^-22 relative error, far inside the 1e-5 parity gate); fp64: IEEE division / sqrt.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+template <typename T>
+struct Tiny;
+template <>
+struct Tiny<float> {
+  static constexpr float v = 1e-30f;
+};
+template <>
+struct Tiny<double> {
+  static constexpr double v = 1e-300;
+};
+
+__device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
+
+// ----------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk TMA (cp.async.bulk, SASS: UBLKCP) — the support table is a contiguous array of
+// 16-byte-aligned rows, so a chunk of rows is one linear bulk copy; no tensor map is needed.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared::cta bulk copy, completion signalled on `bar` (complete_tx).  bytes % 16 == 0.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+}  // namespace dc

@@ -1,0 +1,277 @@
+// Forward-kinematics feature maps and their Jacobian-transpose products, one query per thread.
+//
+// x = FK(q) follows diffco/model.py (== diffco/robot_fkine.py) and diffco/utils.py of the reference; the
+// J^T products are the closed forms of SURVEY.md §9 (the reference gets them from autograd).  These run in
+// the prologue / epilogue of the fused score kernel (once per query, against N support vectors in the main
+// loop), so they are written for clarity and kept out of line; features live in a strided array (a shared
+// memory column in the fused kernel, a global row in dc_fk_forward).
+#pragma once
+
+#include "dc_common.cuh"
+
+namespace dc {
+
+template <typename T>
+struct Strided {
+  T* p;
+  int ld;
+  __device__ __forceinline__ T& operator[](int i) const { return p[(size_t)i * ld]; }
+};
+
+// ---- planar revolute chain: model.py:40-48 -------------------------------------------------------
+template <typename T>
+__device__ void fk_planar_fwd(const double* link, int n, const T* q, Strided<T> x, T tx, T ty, T th0) {
+  // The chain starts at (tx,ty) with heading th0 (zero for the plain chain; the SE(2) base pose for
+  // DC_FK_SE2_BASE_PLANAR_ARM).  theta accumulates like torch.cumsum.
+  T th = th0, px = tx, py = ty;
+  for (int i = 0; i < n; ++i) {
+    th += q[i];
+    T s, c;
+    sincos_t(th, &s, &c);
+    px += (T)link[i] * c;
+    py += (T)link[i] * s;
+    x[2 * i] = px;
+    x[2 * i + 1] = py;
+  }
+}
+
+// g_q[i] = sum_{j>=i} -gx_j (y_j - y_{i-1}) + gy_j (x_j - x_{i-1}); p_{-1} = (ox, oy).
+template <typename T>
+__device__ void fk_planar_vjp(int n, Strided<T> x, Strided<T> g, T ox, T oy, T* gq) {
+  T A = 0, Gx = 0, Gy = 0;
+  for (int i = n - 1; i >= 0; --i) {
+    T px = x[2 * i], py = x[2 * i + 1];
+    T gx = g[2 * i], gy = g[2 * i + 1];
+    A += gy * px - gx * py;
+    Gx += gx;
+    Gy += gy;
+    T qx = (i > 0) ? x[2 * i - 2] : ox;
+    T qy = (i > 0) ? x[2 * i - 1] : oy;
+    gq[i] = A + Gx * qy - Gy * qx;
+  }
+}
+
+// ---- SE(2) rigid body: model.py:90-93, utils.py:40-48 ---------------------------------------------
+template <typename T>
+__device__ void fk_se2_fwd(const dc_fk_desc& fk, const T* q, Strided<T> x) {
+  T s, c;
+  sincos_t(q[2], &s, &c);
+  for (int j = 0; j < fk.n_keypoints; ++j) {
+    T kx = (T)fk.keypoints[0][j], ky = (T)fk.keypoints[1][j];
+    x[2 * j] = c * kx - s * ky + q[0];
+    x[2 * j + 1] = s * kx + c * ky + q[1];
+  }
+}
+template <typename T>
+__device__ void fk_se2_vjp(int m, const T* q, Strided<T> x, Strided<T> g, T* gq) {
+  T g0 = 0, g1 = 0, g2 = 0;
+  for (int j = 0; j < m; ++j) {
+    T gx = g[2 * j], gy = g[2 * j + 1];
+    g0 += gx;
+    g1 += gy;
+    g2 += gy * (x[2 * j] - q[0]) - gx * (x[2 * j + 1] - q[1]);
+  }
+  gq[0] = g0;
+  gq[1] = g1;
+  gq[2] = g2;
+}
+
+// ---- SE(3) rigid body: model.py:156-159, utils.py:15-38 (R = Rz(yaw) Ry(pitch) Rx(roll)) -----------
+template <typename T>
+__device__ void fk_se3_fwd(const dc_fk_desc& fk, const T* q, Strided<T> x) {
+  T sr, cr, sp, cp, sy, cy;
+  sincos_t(q[3], &sr, &cr);
+  sincos_t(q[4], &sp, &cp);
+  sincos_t(q[5], &sy, &cy);
+  // Rz*Ry*Rx
+  T r00 = cy * cp, r01 = cy * sp * sr - sy * cr, r02 = cy * sp * cr + sy * sr;
+  T r10 = sy * cp, r11 = sy * sp * sr + cy * cr, r12 = sy * sp * cr - cy * sr;
+  T r20 = -sp, r21 = cp * sr, r22 = cp * cr;
+  for (int j = 0; j < fk.n_keypoints; ++j) {
+    T kx = (T)fk.keypoints[0][j], ky = (T)fk.keypoints[1][j], kz = (T)fk.keypoints[2][j];
+    x[3 * j] = r00 * kx + r01 * ky + r02 * kz + q[0];
+    x[3 * j + 1] = r10 * kx + r11 * ky + r12 * kz + q[1];
+    x[3 * j + 2] = r20 * kx + r21 * ky + r22 * kz + q[2];
+  }
+}
+template <typename T>
+__device__ void fk_se3_vjp(int m, const T* q, Strided<T> x, Strided<T> g, T* gq) {
+  T f0 = 0, f1 = 0, f2 = 0, m0 = 0, m1 = 0, m2 = 0;  // force and moment (about the body origin) of g
+  for (int j = 0; j < m; ++j) {
+    T gx = g[3 * j], gy = g[3 * j + 1], gz = g[3 * j + 2];
+    T rx = x[3 * j] - q[0], ry = x[3 * j + 1] - q[1], rz = x[3 * j + 2] - q[2];
+    f0 += gx;
+    f1 += gy;
+    f2 += gz;
+    m0 += ry * gz - rz * gy;
+    m1 += rz * gx - rx * gz;
+    m2 += rx * gy - ry * gx;
+  }
+  T sp, cp, sy, cy;
+  sincos_t(q[4], &sp, &cp);
+  sincos_t(q[5], &sy, &cy);
+  gq[0] = f0;
+  gq[1] = f1;
+  gq[2] = f2;
+  gq[3] = cy * cp * m0 + sy * cp * m1 - sp * m2;  // roll axis  Rz Ry e_x
+  gq[4] = -sy * m0 + cy * m1;                     // pitch axis Rz e_y
+  gq[5] = m2;                                     // yaw axis   e_z
+}
+
+// ---- serial standard-DH arms: utils.py:66-77, model.py:225-241 / 366-383 / 430-453 / 486-503 --------
+// Affine frame [R|t] kept as 12 scalars.  `zo` (optional) receives, per joint, the axis z_i and origin o_i of
+// the frame *before* joint i — what the revolute-joint Jacobian column z_i x (p - o_i) needs.
+template <typename T>
+__device__ void fk_dh_arm_fwd(const dc_dh_arm& arm, const T* q, Strided<T> x, T* zo) {
+  T R[9], t[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[3 * r + c] = (T)arm.base[4 * r + c];
+    t[r] = (T)arm.base[4 * r + 3];
+  }
+  const T ox = (T)arm.offset[0], oy = (T)arm.offset[1], oz = (T)arm.offset[2];
+  for (int i = 0; i < arm.n_joints; ++i) {
+    if (zo) {
+      zo[6 * i + 0] = R[2];
+      zo[6 * i + 1] = R[5];
+      zo[6 * i + 2] = R[8];
+      zo[6 * i + 3] = t[0];
+      zo[6 * i + 4] = t[1];
+      zo[6 * i + 5] = t[2];
+    }
+    T st, ct;
+    sincos_t(q[arm.joint_index[i]] + (T)arm.theta0[i], &st, &ct);
+    const T sa = (T)arm.s_alpha[i], ca = (T)arm.c_alpha[i], a = (T)arm.a[i], d = (T)arm.d[i];
+    // DH_i = [[ct, -st ca, st sa, a ct], [st, ct ca, -ct sa, a st], [0, sa, ca, d]]
+    const T m00 = ct, m01 = -st * ca, m02 = st * sa, m03 = a * ct;
+    const T m10 = st, m11 = ct * ca, m12 = -ct * sa, m13 = a * st;
+    const T m21 = sa, m22 = ca, m23 = d;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const T r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
+      R[3 * r] = r0 * m00 + r1 * m10;
+      R[3 * r + 1] = r0 * m01 + r1 * m11 + r2 * m21;
+      R[3 * r + 2] = r0 * m02 + r1 * m12 + r2 * m22;
+      t[r] = r0 * m03 + r1 * m13 + r2 * m23 + t[r];
+    }
+    const int slot = arm.out_slot[i];
+    if (slot >= 0) {
+      x[3 * slot] = t[0] + ox;
+      x[3 * slot + 1] = t[1] + oy;
+      x[3 * slot + 2] = t[2] + oz;
+    }
+  }
+  for (int k = 0; k < arm.n_tool; ++k) {
+    const T ux = (T)arm.tool[k][0], uy = (T)arm.tool[k][1], uz = (T)arm.tool[k][2];
+    const int slot = arm.tool_slot[k];
+    x[3 * slot] = R[0] * ux + R[1] * uy + R[2] * uz + t[0] + ox;
+    x[3 * slot + 1] = R[3] * ux + R[4] * uy + R[5] * uz + t[1] + oy;
+    x[3 * slot + 2] = R[6] * ux + R[7] * uy + R[8] * uz + t[2] + oz;
+  }
+}
+
+// g_q[j_i] = z_i . ( sum_{p attached at frame >= i} (p - o_i) x g_p ) = z_i . (Mom - o_i x Frc)
+template <typename T>
+__device__ void fk_dh_arm_vjp(const dc_dh_arm& arm, const T* q, Strided<T> x, Strided<T> g, T* gq) {
+  T zo[6 * DC_MAX_ARM_JOINTS];
+  // Recompute the frames (cheaper than keeping 48 values alive across the pair loop).  This rewrites x with
+  // the values it already holds (same thread, same inputs), which keeps a single forward code path.
+  fk_dh_arm_fwd<T>(arm, q, x, zo);
+  const T ox = (T)arm.offset[0], oy = (T)arm.offset[1], oz = (T)arm.offset[2];
+  T F0 = 0, F1 = 0, F2 = 0, M0 = 0, M1 = 0, M2 = 0;
+  auto add_point = [&](int slot) {
+    const T px = x[3 * slot] - ox, py = x[3 * slot + 1] - oy, pz = x[3 * slot + 2] - oz;
+    const T gx = g[3 * slot], gy = g[3 * slot + 1], gz = g[3 * slot + 2];
+    F0 += gx;
+    F1 += gy;
+    F2 += gz;
+    M0 += py * gz - pz * gy;
+    M1 += pz * gx - px * gz;
+    M2 += px * gy - py * gx;
+  };
+  for (int k = 0; k < arm.n_tool; ++k) add_point(arm.tool_slot[k]);
+  for (int i = arm.n_joints - 1; i >= 0; --i) {
+    if (arm.out_slot[i] >= 0) add_point(arm.out_slot[i]);
+    const T zx = zo[6 * i], zy = zo[6 * i + 1], zz = zo[6 * i + 2];
+    const T px = zo[6 * i + 3], py = zo[6 * i + 4], pz = zo[6 * i + 5];
+    const T c0 = M0 - (py * F2 - pz * F1);
+    const T c1 = M1 - (pz * F0 - px * F2);
+    const T c2 = M2 - (px * F1 - py * F0);
+    gq[arm.joint_index[i]] = zx * c0 + zy * c1 + zz * c2;
+  }
+}
+
+// ---- dispatch ----------------------------------------------------------------------------------------
+template <typename T>
+__device__ __noinline__ void fk_forward(const dc_fk_desc& fk, const T* q, T* xp, int ld) {
+  Strided<T> x{xp, ld};
+  switch (fk.type) {
+    case DC_FK_NONE:
+      for (int i = 0; i < fk.dof; ++i) x[i] = q[i];
+      break;
+    case DC_FK_PLANAR_CHAIN:
+      fk_planar_fwd<T>(fk.link_length, fk.n_links, q, x, (T)0, (T)0, (T)0);
+      break;
+    case DC_FK_SE2_BODY:
+      fk_se2_fwd<T>(fk, q, x);
+      break;
+    case DC_FK_SE3_BODY:
+      fk_se3_fwd<T>(fk, q, x);
+      break;
+    case DC_FK_DH_ARMS:
+      for (int a = 0; a < fk.n_arms; ++a) fk_dh_arm_fwd<T>(fk.arms[a], q, x, nullptr);
+      break;
+    case DC_FK_SE2_BASE_PLANAR_ARM: {
+      fk_se2_fwd<T>(fk, q, x);
+      // chain in the base frame == chain with initial angle theta and origin (x, y)
+      Strided<T> xa{xp + (size_t)2 * fk.n_keypoints * ld, ld};
+      fk_planar_fwd<T>(fk.link_length, fk.n_links, q + 3, xa, q[0], q[1], q[2]);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+template <typename T>
+__device__ __noinline__ void fk_vjp(const dc_fk_desc& fk, const T* q, T* xp, int ldx, T* gp, int ldg, T* gq) {
+  Strided<T> x{xp, ldx};
+  Strided<T> g{gp, ldg};
+  switch (fk.type) {
+    case DC_FK_NONE:
+      for (int i = 0; i < fk.dof; ++i) gq[i] = g[i];
+      break;
+    case DC_FK_PLANAR_CHAIN:
+      fk_planar_vjp<T>(fk.n_links, x, g, (T)0, (T)0, gq);
+      break;
+    case DC_FK_SE2_BODY:
+      fk_se2_vjp<T>(fk.n_keypoints, q, x, g, gq);
+      break;
+    case DC_FK_SE3_BODY:
+      fk_se3_vjp<T>(fk.n_keypoints, q, x, g, gq);
+      break;
+    case DC_FK_DH_ARMS:
+      for (int a = 0; a < fk.n_arms; ++a) fk_dh_arm_vjp<T>(fk.arms[a], q, x, g, gq);
+      break;
+    case DC_FK_SE2_BASE_PLANAR_ARM: {
+      const int mb = fk.n_keypoints;
+      fk_se2_vjp<T>(mb, q, x, g, gq);
+      Strided<T> xa{xp + (size_t)2 * mb * ldx, ldx};
+      Strided<T> ga{gp + (size_t)2 * mb * ldg, ldg};
+      // The arm points rotate with the base: they contribute to (x, y, theta) exactly like body key points,
+      // and to the arm joints through the planar-chain formula with p_{-1} = base origin.
+      T a3[3];
+      fk_se2_vjp<T>(fk.n_links, q, xa, ga, a3);
+      gq[0] += a3[0];
+      gq[1] += a3[1];
+      gq[2] += a3[2];
+      fk_planar_vjp<T>(fk.n_links, xa, ga, q[0], q[1], gq + 3);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+}  // namespace dc

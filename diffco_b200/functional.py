@@ -1,0 +1,224 @@
+"""Tensor-facing wrappers over the C ABI: device buffers, streams and autograd plumbing only.
+
+Everything numeric happens in libdiffco_b200.so; PyTorch supplies device memory (``torch.empty``), the current
+CUDA stream and the autograd graph.  There is deliberately no CPU / eager fallback: without CUDA these
+functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DC_F32, DC_F64, DC_GRAD_JAC, DC_GRAD_NONE, DC_GRAD_SUM, FkDesc, KernelDesc, Supports
+
+_DTYPES = {torch.float32: DC_F32, torch.float64: DC_F64}
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("diffco_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback for this path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPES[dtype]
+    except KeyError:
+        raise TypeError(f"diffco_b200 supports float32 and float64, got {dtype}") from None
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def none_fk(n_features: int) -> FkDesc:
+    """FK descriptor for ``transform=None`` (kernel_perceptrons.py:36): the input rows are the features."""
+    d = FkDesc()
+    d.type = _lib.DC_FK_NONE
+    d.dof = n_features
+    d.n_points = n_features
+    d.point_dim = 1
+    return d
+
+
+class SupportSet:
+    """Support vectors + weights packed for the fused kernels (row n = [-s_n | w_n], 16-byte aligned rows).
+
+    ``s_feat`` is ``support_transformed.reshape(N, -1)``, ``weights`` is ``gains`` / ``rbf_nodes`` with shape (N,) or
+    (N, C).  The packed table lives in HBM for the lifetime of the object (N*(F+C) elements, <= 0.4 MB for every
+    configuration in BASELINE.json) and is re-read by every launch from L2.
+    """
+
+    def __init__(self, s_feat: torch.Tensor, weights: torch.Tensor, device: Optional[torch.device] = None):
+        device = device or _require_cuda()
+        lib = _lib.load()
+        s = s_feat.detach().reshape(s_feat.shape[0], -1)
+        w = weights.detach()
+        if w.ndim == 1:
+            w = w[:, None]
+        if w.shape[0] != s.shape[0]:
+            raise ValueError(f"weights have {w.shape[0]} rows, supports have {s.shape[0]}")
+        dtype = s.dtype
+        code = _dtype_code(dtype)
+        s = s.to(device=device, dtype=dtype).contiguous()
+        w = w.to(device=device, dtype=dtype).contiguous()
+        self.n, self.n_features = s.shape
+        self.n_class = w.shape[1]
+        f_pad, row = C.c_int32(), C.c_int32()
+        _lib.check(lib.dc_supports_layout(self.n_features, self.n_class, code, C.byref(f_pad), C.byref(row)),
+                   "dc_supports_layout")
+        self.table = torch.empty((self.n, row.value), dtype=dtype, device=device)
+        with torch.cuda.device(device):
+            _lib.check(lib.dc_pack_supports(s.data_ptr(), w.data_ptr(), self.n, self.n_features, self.n_class, code,
+                                            self.table.data_ptr(), _stream_ptr(device)), "dc_pack_supports")
+        self.dtype = dtype
+        self.device = device
+        self.desc = Supports(self.table.data_ptr(), self.n, self.n_features, self.n_class, f_pad.value, row.value, code, 0)
+
+
+def score_grad(fk: FkDesc, kernel: KernelDesc, sv: SupportSet, q: torch.Tensor, grad_mode: int = DC_GRAD_NONE,
+               grad_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """One launch of the fused hot path.  q: (B, D) on ``sv.device`` with ``sv.dtype``.
+
+    Returns ``score`` (B, C) and, per ``grad_mode``, ``None`` | grad (B, D) | Jacobian (B, C, D).
+    """
+    lib = _lib.load()
+    if q.device != sv.device or q.dtype != sv.dtype:
+        raise ValueError(f"q must be {sv.dtype} on {sv.device}, got {q.dtype} on {q.device}")
+    if q.ndim != 2 or q.shape[1] != fk.dof:
+        raise ValueError(f"q must have shape (B, {fk.dof}), got {tuple(q.shape)}")
+    if fk.n_features != sv.n_features:
+        raise ValueError(f"feature map yields {fk.n_features} features, support set has {sv.n_features}")
+    q = q.detach().contiguous()
+    B = q.shape[0]
+    score = torch.empty((B, sv.n_class), dtype=sv.dtype, device=sv.device)
+    grad = None
+    if grad_mode == DC_GRAD_SUM:
+        grad = torch.empty((B, fk.dof), dtype=sv.dtype, device=sv.device)
+    elif grad_mode == DC_GRAD_JAC:
+        grad = torch.empty((B, sv.n_class, fk.dof), dtype=sv.dtype, device=sv.device)
+    go = None
+    if grad_out is not None:
+        if grad_mode != DC_GRAD_SUM:
+            raise ValueError("grad_out is only meaningful with DC_GRAD_SUM")
+        go = grad_out.detach().to(device=sv.device, dtype=sv.dtype).reshape(B, sv.n_class).contiguous()
+    if B == 0:
+        return score, grad
+    with torch.cuda.device(sv.device):
+        st = lib.dc_score_grad(C.byref(fk), C.byref(kernel), C.byref(sv.desc), q.data_ptr(), B, score.data_ptr(),
+                               _ptr(grad), _ptr(go), grad_mode, None, _stream_ptr(sv.device))
+    _lib.check(st, "dc_score_grad")
+    return score, grad
+
+
+def kernel_matrix(kernel: KernelDesc, xa: torch.Tensor, xb: torch.Tensor) -> torch.Tensor:
+    """K[i, j] = k(|xa_i - xb_j|^2) on flattened feature rows (training rows, fit_poly, jump-start block)."""
+    lib = _lib.load()
+    device = _require_cuda() if not xa.is_cuda else xa.device
+    dtype = xa.dtype
+    code = _dtype_code(dtype)
+    a = xa.detach().reshape(xa.shape[0], -1).to(device=device, dtype=dtype).contiguous()
+    b = xb.detach().reshape(xb.shape[0], -1).to(device=device, dtype=dtype).contiguous()
+    if a.shape[1] != b.shape[1]:
+        raise ValueError(f"feature mismatch: {a.shape[1]} vs {b.shape[1]}")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=dtype, device=device)
+    if out.numel():
+        with torch.cuda.device(device):
+            _lib.check(lib.dc_kernel_matrix(C.byref(kernel), a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], a.shape[1],
+                                            code, out.data_ptr(), _stream_ptr(device)), "dc_kernel_matrix")
+    return out
+
+
+def fk_forward(fk: FkDesc, q: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    q = q.detach().contiguous()
+    out = torch.empty((q.shape[0], fk.n_features), dtype=q.dtype, device=q.device)
+    if q.shape[0]:
+        with torch.cuda.device(q.device):
+            _lib.check(lib.dc_fk_forward(C.byref(fk), q.data_ptr(), q.shape[0], _dtype_code(q.dtype), out.data_ptr(),
+                                         _stream_ptr(q.device)), "dc_fk_forward")
+    return out
+
+
+def fk_vjp(fk: FkDesc, q: torch.Tensor, g_x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    q = q.detach().contiguous()
+    g_x = g_x.detach().to(dtype=q.dtype, device=q.device).reshape(q.shape[0], fk.n_features).contiguous()
+    out = torch.empty_like(q)
+    if q.shape[0]:
+        with torch.cuda.device(q.device):
+            _lib.check(lib.dc_fk_vjp(C.byref(fk), q.data_ptr(), q.shape[0], _dtype_code(q.dtype), g_x.data_ptr(),
+                                     out.data_ptr(), _stream_ptr(q.device)), "dc_fk_vjp")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------
+# autograd
+# --------------------------------------------------------------------------------------------------------
+
+
+class _ScoreFunction(torch.autograd.Function):
+    """score = evaluator(q) with the analytic Jacobian stashed for backward.
+
+    ``evaluator(q_dev, want_jac) -> (score (B,C), jac (B,C,D) | None)`` runs the fused CUDA kernel.  backward is
+    ``einsum('bc,bcd->bd')`` — pure torch ops on the stashed Jacobian — so it also works when autograd batches the
+    upstream gradient (``torch.autograd.functional.jacobian(vectorize=True)``, diffco/optim.py:211-216).  The
+    Jacobian is a constant w.r.t. autograd: second derivatives (optim.py:380-391, trust-constr Hessians) are not
+    provided and fail loudly instead of silently returning zeros.
+    """
+
+    @staticmethod
+    def forward(q, evaluator):
+        score, jac = evaluator(q, q.requires_grad or torch.is_grad_enabled())
+        return score, jac
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        _, jac = output
+        ctx.save_for_backward(jac)
+        ctx.mark_non_differentiable(jac)
+        ctx.set_materialize_grads(False)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_score, _grad_jac):
+        (jac,) = ctx.saved_tensors
+        if grad_score is None:
+            return None, None
+        return torch.einsum("...bc,bcd->...bd", grad_score.to(jac.dtype), jac), None
+
+
+def differentiable_score(q: torch.Tensor, evaluator) -> torch.Tensor:
+    """Run ``evaluator`` on q (any device / dtype handled by the evaluator) with autograd support."""
+    if q.requires_grad and torch.is_grad_enabled():
+        score, _ = _ScoreFunction.apply(q, evaluator)
+        return score
+    score, _ = evaluator(q, False)
+    return score
+
+
+class _FkFunction(torch.autograd.Function):
+    """fkine with the J^T product from dc_fk_vjp (first derivatives only)."""
+
+    @staticmethod
+    def forward(q, runner):
+        return runner.forward(q)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        q, runner = inputs
+        ctx.runner = runner
+        ctx.save_for_backward(q)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_x):
+        (q,) = ctx.saved_tensors
+        return ctx.runner.vjp(q, grad_x), None

@@ -1,0 +1,174 @@
+/*
+ * diffco_b200 — C ABI of the B200-native DiffCo collision-score hot path.
+ *
+ * This is the drop-in boundary.  The reference (ucsdarclab/diffco) is pure Python and has no
+ * FFI layer; the functions below are what a Python binding for its hot path binds (INTEGRATION.md shows the
+ * ctypes stubs), one entry point per reference call site:
+ *
+ *   dc_score_grad      <- DiffCo.score_original      diffco/kernel_perceptrons.py:362-370
+ *                         DiffCo.poly_score          diffco/kernel_perceptrons.py:309-319
+ *                         MultiDiffCo.score/rbf_score diffco/deprecated/MultiDiffCo.py:118-123,156-170
+ *                         + the autograd backward the optimisers run through them (diffco/optim.py:86-103,209-218)
+ *   dc_kernel_matrix   <- kernel_func(X_t[i], X_t)   diffco/kernel_perceptrons.py:118 (training row)
+ *                         rbf_kernel(S, S)           diffco/kernel_perceptrons.py:280 (fit_poly)
+ *                         kernel_func(S, novel)      diffco/kernel_perceptrons.py:246 (jump start)
+ *   dc_fk_forward/vjp  <- *.fkine                    diffco/model.py:40-48,90-93,156-159,225-241,366-383,430-453,486-503
+ *   dc_perceptron_train<- DiffCo.train_perceptron    diffco/kernel_perceptrons.py:98-158
+ *
+ * Conventions: all pointers except descriptors are DEVICE pointers to row-major contiguous arrays of `dtype`
+ * (DC_F32 / DC_F64); descriptors are plain-old-data structs in HOST memory, copied by value into the launch.
+ * Every call enqueues work on `stream` and returns without synchronising; return value 0 = ok, <0 = dc_status.
+ * No torch types, no exceptions, no global state.
+ */
+#ifndef DIFFCO_B200_H
+#define DIFFCO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DC_ABI_VERSION 1
+
+#define DC_MAX_DOF 16
+#define DC_MAX_LINKS 16
+#define DC_MAX_KEYPOINTS 16
+#define DC_MAX_ARMS 2
+#define DC_MAX_ARM_JOINTS 8
+#define DC_MAX_TOOL_POINTS 2
+#define DC_MAX_FEATURES 64
+#define DC_MAX_CLASSES 8
+
+typedef struct CUstream_st* dc_stream_t; /* == cudaStream_t */
+
+typedef enum dc_status {
+  DC_OK = 0,
+  DC_ERR_INVALID_ARG = -1,
+  DC_ERR_UNSUPPORTED = -2,
+  DC_ERR_CUDA = -3,
+  DC_ERR_NO_DEVICE = -4
+} dc_status;
+
+typedef enum dc_dtype { DC_F32 = 0, DC_F64 = 1 } dc_dtype;
+
+/* Forward-kinematics feature maps q[B,dof] -> X[B, n_points*point_dim] (diffco/model.py). */
+typedef enum dc_fk_type {
+  DC_FK_NONE = 0,               /* transform=None: the configuration itself is the feature vector     */
+  DC_FK_PLANAR_CHAIN = 1,       /* RevolutePlanarRobot.fkine           model.py:40-48                   */
+  DC_FK_SE2_BODY = 2,           /* RigidPlanarBody.fkine               model.py:90-93                   */
+  DC_FK_SE3_BODY = 3,           /* RigidBody.fkine                     model.py:156-159                 */
+  DC_FK_DH_ARMS = 4,            /* Baxter L/R/dual, Panda, DualPanda   model.py:225-241,366-383,430-503 */
+  DC_FK_SE2_BASE_PLANAR_ARM = 5 /* SE(2) base carrying a planar chain  (BASELINE.json configs[3])       */
+} dc_fk_type;
+
+/* One serial standard-DH arm (utils.DH2mat, diffco/utils.py:66-77). */
+typedef struct dc_dh_arm {
+  int32_t n_joints;
+  int32_t n_tool;                          /* points rigidly attached to the last frame (Panda fingers)   */
+  int32_t joint_index[DC_MAX_ARM_JOINTS];  /* column of q driving joint i                                 */
+  int32_t out_slot[DC_MAX_ARM_JOINTS];     /* output point index of frame i's origin, or -1 (fk_mask)     */
+  int32_t tool_slot[DC_MAX_TOOL_POINTS];
+  double a[DC_MAX_ARM_JOINTS];
+  double d[DC_MAX_ARM_JOINTS];
+  double s_alpha[DC_MAX_ARM_JOINTS];
+  double c_alpha[DC_MAX_ARM_JOINTS];
+  double theta0[DC_MAX_ARM_JOINTS];
+  double base[12];                         /* row-major 3x4 [R|t] pre-multiplied base (identity if unused) */
+  double offset[3];                        /* translation added to the outputs (DualPandaFK bases)        */
+  double tool[DC_MAX_TOOL_POINTS][3];
+} dc_dh_arm;
+
+typedef struct dc_fk_desc {
+  int32_t type;       /* dc_fk_type */
+  int32_t dof;        /* D */
+  int32_t n_points;   /* M */
+  int32_t point_dim;  /* d in {1,2,3}; features F = M*d (type NONE: F = dof) */
+  int32_t n_arms;
+  int32_t n_keypoints;
+  int32_t n_links;
+  int32_t reserved;
+  double link_length[DC_MAX_LINKS];
+  double keypoints[3][DC_MAX_KEYPOINTS]; /* body-frame key points, row r = coordinate r */
+  dc_dh_arm arms[DC_MAX_ARMS];
+} dc_fk_desc;
+
+/* Radial kernels (diffco/kernel.py). */
+typedef enum dc_kernel_kind {
+  DC_K_RQ = 1,           /* RQKernel      kernel.py:12-29   k = (1 + gamma/p r^2)^-p   param=gamma order=p */
+  DC_K_POLYHARMONIC = 2, /* Polyharmonic  kernel.py:59-79   k = r^k/eps | r^k log r/eps param=eps   order=k */
+  DC_K_MULTIQUADRIC = 3  /* MultiQuadratic kernel.py:45-57  k = sqrt(r^2/eps^2 + 1)    param=eps          */
+} dc_kernel_kind;
+
+typedef struct dc_kernel_desc {
+  int32_t kind;
+  int32_t order;
+  double param;
+} dc_kernel_desc;
+
+/* Support set packed for the fused kernels: row n = [-s_n[0..F) zero-padded to f_pad | w[n,0..C) zero-padded]. */
+typedef struct dc_supports {
+  const void* table;   /* device, [n][row_stride] of dtype, 16-byte aligned rows */
+  int64_t n;           /* N support vectors */
+  int32_t n_features;  /* F */
+  int32_t n_class;     /* C */
+  int32_t f_pad;
+  int32_t row_stride;  /* elements per row */
+  int32_t dtype;
+  int32_t reserved;
+} dc_supports;
+
+typedef enum dc_grad_mode {
+  DC_GRAD_NONE = 0, /* score only                                                                   */
+  DC_GRAD_SUM = 1,  /* grad[B,D]   = sum_c grad_out[b,c] * d score[b,c]/dq   (grad_out NULL = ones) */
+  DC_GRAD_JAC = 2   /* grad[B,C,D] = d score[b,c]/dq                                                */
+} dc_grad_mode;
+
+int dc_abi_version(void);
+const char* dc_status_string(int status);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches evidence). */
+int64_t dc_launch_count(void);
+
+/* Layout of the packed support table for (F, C, dtype). */
+int dc_supports_layout(int32_t n_features, int32_t n_class, int32_t dtype, int32_t* f_pad, int32_t* row_stride);
+/* Pack S_feat[N,F] (= support_transformed.reshape(N,-1)) and W[N,C] (gains or rbf_nodes) into `table`. */
+int dc_pack_supports(const void* s_feat, const void* w, int64_t n, int32_t n_features, int32_t n_class, int32_t dtype,
+                     void* table, dc_stream_t stream);
+
+/*
+ * The hot path.  score[B,C] = sum_n w[n,c] k(|FK(q_b) - s_n|^2) and, per grad_mode, its gradient w.r.t. q.
+ * fk->type == DC_FK_NONE: q is the feature matrix X[B,F] itself (poly_score(transformed_point=...),
+ * kernel_perceptrons.py:316-317) and gradients are w.r.t. X.
+ * workspace: optional device scratch of dc_score_workspace_bytes() bytes (needed only when the launch splits the
+ * support set across CTAs, i.e. small B); may be NULL when that returns 0.
+ */
+int64_t dc_score_workspace_bytes(const dc_fk_desc* fk, const dc_supports* sv, int64_t batch, int32_t grad_mode);
+int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
+                  int64_t batch, void* score, void* grad, const void* grad_out, int32_t grad_mode, void* workspace,
+                  dc_stream_t stream);
+
+/* K[Na,Nb] = k(|xa_i - xb_j|^2) on pre-transformed features (training rows, fit_poly, jump-start block). */
+int dc_kernel_matrix(const dc_kernel_desc* kernel, const void* xa, int64_t na, const void* xb, int64_t nb,
+                     int32_t n_features, int32_t dtype, void* k_out, dc_stream_t stream);
+
+/* X[B,F] = FK(q[B,D]);  gq[B,D] = J_FK(q)^T gX[B,F]. */
+int dc_fk_forward(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, void* x_out, dc_stream_t stream);
+int dc_fk_vjp(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, const void* g_x, void* g_q,
+              dc_stream_t stream);
+
+/*
+ * Greedy kernel-perceptron training, the whole loop in one launch (DiffCo.train_perceptron,
+ * kernel_perceptrons.py:98-133; legacy_multi != 0: MultiDiffCo.train_perceptron, deprecated/MultiDiffCo.py:50-83).
+ * x_feat[N,F] are the transformed training points, y[N,C] the +-1 labels.  gains[N,C], hypothesis[N,C],
+ * kernel_matrix[N,N] and diag[N] (the diagonal of kernel_matrix; 0 == "row not computed yet") are IN/OUT: zero them
+ * for a fresh fit, or pre-load them for the jump-start update (kernel_perceptrons.py:222-269).
+ * iterations_out[2] (device): index of the last iteration executed, number of kernel rows evaluated.
+ */
+int dc_perceptron_train(const dc_kernel_desc* kernel, const void* x_feat, const void* y, int64_t n, int32_t n_features,
+                        int32_t n_class, int32_t dtype, double beta, int64_t max_iteration, void* gains, void* hypothesis,
+                        void* kernel_matrix, void* diag, int32_t legacy_multi, int64_t* iterations_out, dc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFCO_B200_H */

@@ -1,0 +1,278 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference (imported from
+/root/reference through oracle/ref_loader.py) on seeded inputs.  TEST INFRASTRUCTURE ONLY.
+
+    python -m oracle.make_golden            # in the build container (needs /root/reference)
+
+The fixtures hold inputs AND the reference's outputs (float64), so the GPU box — which has no /root/reference — can
+check both the oracle restatement (tests/test_oracle_vs_golden.py, CPU) and the CUDA path (tests/test_gpu_*.py).
+The reference ships no golden vectors of its own for this path, so these are the pin.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def gen_kernels(ns):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(5, 3, 2, generator=g, dtype=torch.float64)
+    s = torch.randn(7, 3, 2, generator=g, dtype=torch.float64)
+    s[2] = x[1]  # an exact coincidence: r == 0 (Polyharmonic sub-gradient / even-k NaN->0 edge)
+    out = {"x": _np(x), "s": _np(s)}
+    K = ns.kernel
+    cases = {
+        "rq_g10_p2": K.RQKernel(10.0), "rq_g3_p3": K.RQKernel(3.0, 3), "rq_g1_p1": K.RQKernel(1.0, 1),
+        "ph_k1_e1": K.Polyharmonic(1, 1.0), "ph_k3_e05": K.Polyharmonic(3, 0.5), "ph_k2_e1": K.Polyharmonic(2, 1.0),
+        "ph_k1_e001": K.Polyharmonic(1, 0.01),
+    }
+    for name, k in cases.items():
+        out[name] = _np(k(x, s))
+        try:  # rank-deficient query: shape quirks (kernel.py:18-27); Polyharmonic's .view raises here (kernel.py:76)
+            out[name + "_single"] = _np(k(x[0], s))
+        except TypeError:
+            pass
+    mq = K.MultiQuadratic(0.7)
+    out["mq_e07"] = _np(mq(x.reshape(5, -1), s.reshape(7, -1)))
+    out["mq_e07_single"] = _np(mq(x.reshape(5, -1)[0], s.reshape(7, -1)))
+    # autograd gradients of sum(K w) wrt x for the three inference kernels
+    w = torch.randn(7, generator=g, dtype=torch.float64)
+    out["w"] = _np(w)
+    for name, k in (("rq_g10_p2", cases["rq_g10_p2"]), ("ph_k1_e1", cases["ph_k1_e1"]), ("ph_k3_e05", cases["ph_k3_e05"])):
+        xv = x.clone().requires_grad_(True)
+        (k(xv, s) @ w).sum().backward()
+        out[name + "_gradx"] = _np(xv.grad)
+    xv = x.reshape(5, -1).clone().requires_grad_(True)
+    (mq(xv, s.reshape(7, -1)) @ w).sum().backward()
+    out["mq_e07_gradx"] = _np(xv.grad)
+    np.savez_compressed(os.path.join(OUT, "kernels.npz"), **out)
+
+
+def gen_fk(ns):
+    g = torch.Generator().manual_seed(12)
+    M = ns.model
+    out = {}
+
+    def sample(limits, n=6):
+        lim = limits.double()
+        return torch.rand(n, lim.shape[0], generator=g, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+
+    def record(name, robot, q, dtype=torch.float64, module="model"):
+        qv = q.to(dtype).clone().requires_grad_(True)
+        pts = robot.fkine(qv)
+        wts = torch.randn(pts.shape, generator=g, dtype=torch.float64).to(dtype)
+        (pts * wts).sum().backward()
+        out[name + "_q"], out[name + "_x"], out[name + "_gx"], out[name + "_gq"] = _np(q), _np(pts.double()), _np(wts.double()), _np(qv.grad.double())
+
+    for dof, L in ((2, 1.0), (3, [1.0, 0.8, 0.6]), (7, 1.0)):
+        r = M.RevolutePlanarRobot(L, 0.3, dof=dof) if not isinstance(L, list) else M.RevolutePlanarRobot(L, 0.3)
+        record(f"planar{dof}", r, sample(r.limits))
+    parts = [("box", (0.5, 0.2), (1, 1)), ("box", (-0.4, 0.3), (1, 1)), ("box", (0.1, -0.6), (1, 1)),
+             ("box", (-0.3, -0.2), (1, 1)), ("box", (0.7, 0.7), (1, 1))]
+    r = M.RigidPlanarBody(parts)
+    # rot_2d allocates float32 (utils.py:41): the reference's SE(2) map only runs in float32
+    record("se2", r, sample(r.limits), dtype=torch.float32)
+    # RigidBody.__init__ needs trimesh; fkine only needs dof/keypoints (model.py:156-159)
+    r = object.__new__(M.RigidBody)
+    r.dof = 6
+    c = [[sx * 0.5, sy * 0.3, sz * 0.2] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]
+    r.keypoints = torch.FloatTensor(c).T
+    r.limits = torch.FloatTensor([[-10, 10]] * 3 + [[-np.pi, np.pi]] * 3)
+    record("se3", r, sample(r.limits), dtype=torch.float32)  # float32 keypoints, matmul does not promote (model.py:158)
+    r = M.BaxterLeftArmFK()
+    record("baxter", r, sample(r.limits))
+    r = M.BaxterRightArmFK()
+    record("baxter_right", r, sample(r.limits))
+    r = M.BaxterDualArmFK()  # float32 only: arm_bases is float32 and torch.matmul does not promote (model.py:376)
+    record("baxter_dual", r, sample(r.limits), dtype=torch.float32)
+    r = M.PandaFK()
+    record("panda", r, sample(r.limits))
+    r = ns.robot_fkine.PandaFK()  # older twin: 5 control points (robot_fkine.py:428-444)
+    record("panda5", r, sample(r.limits))
+    r = M.DualPandaFK()
+    record("dual_panda", r, sample(r.limits))
+    np.savez_compressed(os.path.join(OUT, "fk.npz"), **out)
+
+
+def _circle_labels(pts):
+    hit = torch.zeros(len(pts), dtype=torch.bool)
+    for (cx, cy), rad in (((3.0, 2.0), 2.0), ((-2.0, 3.0), 0.8)):
+        hit |= ((pts - torch.tensor([cx, cy], dtype=torch.float64)).norm(dim=2) < rad).any(dim=1)
+    return hit.double() * 2 - 1
+
+
+def gen_perceptron(ns):
+    """Train the reference DiffCo on small planar problems; record the selected indices, gains, hypothesis, fit_poly
+    nodes, and score / poly_score values + autograd gradients on held-out queries."""
+    M, K, P = ns.model, ns.kernel, ns.kernel_perceptrons
+    out = {}
+    for tag, dof, n_train, seed in (("p2", 2, 400, 21), ("p7", 7, 700, 22)):
+        g = torch.Generator().manual_seed(seed)
+        robot = M.RevolutePlanarRobot(1.0, 0.3, dof=dof)
+        X = (torch.rand(n_train, dof, generator=g, dtype=torch.float64) * 2 - 1) * np.pi
+        if dof == 2:
+            pts = robot.fkine(X)
+            y = (((pts - torch.tensor([1.2, 0.8], dtype=torch.float64)).norm(dim=2) < 0.7).any(1)).double() * 2 - 1
+        else:
+            y = _circle_labels(robot.fkine(X))
+        dc = P.DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+        dc.train(X, y, max_iteration=n_train)
+        # indices of the supports inside X (rows are unique)
+        idx = torch.tensor([int(torch.where((X == sp).all(1))[0][0]) for sp in dc.support_points])
+        dc.fit_poly(K.Polyharmonic(1, 1.0), target="label")
+        Q = (torch.rand(24, dof, generator=g, dtype=torch.float64) * 2 - 1) * np.pi
+        Q[0] = dc.support_points[3]  # a query that coincides with a support: r == 0 for Polyharmonic
+        qv = Q.clone().requires_grad_(True)
+        s = dc.score(qv)
+        s.sum().backward()
+        gs = qv.grad.clone()
+        qv = Q.clone().requires_grad_(True)
+        ps = dc.poly_score(qv)
+        ps.sum().backward()
+        gp = qv.grad.clone()
+        out.update({f"{tag}_X": _np(X), f"{tag}_y": _np(y), f"{tag}_idx": _np(idx), f"{tag}_gains": _np(dc.gains),
+                    f"{tag}_hyp": _np(dc.hypothesis), f"{tag}_K": _np(dc.kernel_matrix), f"{tag}_nodes": _np(dc.rbf_nodes),
+                    f"{tag}_Q": _np(Q), f"{tag}_score": _np(s), f"{tag}_score_grad": _np(gs), f"{tag}_poly": _np(ps),
+                    f"{tag}_poly_grad": _np(gp), f"{tag}_single_score": _np(dc.score(Q[5])),
+                    f"{tag}_single_poly": _np(dc.poly_score(Q[5]))})
+        if tag == "p7":
+            # active-learning round: jump-start state for (old supports + novel points) (kernel_perceptrons.py:222-269)
+            novel = (torch.rand(150, dof, generator=g, dtype=torch.float64) * 2 - 1) * np.pi
+            Xu = torch.cat([dc.support_points, novel])
+            yu = torch.cat([dc.y, _circle_labels(robot.fkine(novel))])
+            exist = torch.zeros(len(Xu), dtype=torch.bool)
+            exist[: len(dc.support_points)] = True
+            gains0, _, _, K0, h0, _ = dc.jump_start_initialize(Xu, yu, exist)
+            dc.train(Xu, yu, update=True, exist_mask=exist, max_iteration=len(Xu))
+            idx2 = torch.tensor([int(torch.where((Xu == sp).all(1))[0][0]) for sp in dc.support_points])
+            out.update({"p7u_X": _np(Xu), "p7u_y": _np(yu), "p7u_exist": _np(exist), "p7u_gains0": _np(gains0), "p7u_h0": _np(h0),
+                        "p7u_K0": _np(K0), "p7u_idx": _np(idx2), "p7u_gains": _np(dc.gains), "p7u_hyp": _np(dc.hypothesis)})
+    np.savez_compressed(os.path.join(OUT, "perceptron.npz"), **out)
+
+
+def gen_multiclass(ns):
+    """Legacy 4-class MultiDiffCo on Baxter (deprecated/MultiDiffCo.py) with the FKKernel shim."""
+    M, K = ns.model, ns.kernel
+    g = torch.Generator().manual_seed(31)
+    robot = M.BaxterLeftArmFK()
+    lim = robot.limits.double()
+    X = torch.rand(160, 7, generator=g, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+    pts = robot.fkine(X)
+    centers = torch.tensor([[0.6, 0.2, 0.3], [0.3, -0.5, 0.6], [0.8, 0.0, -0.1], [0.2, 0.6, 0.1]], dtype=torch.float64)
+    radii = torch.tensor([0.45, 0.4, 0.4, 0.35], dtype=torch.float64)
+    Y = torch.stack([((pts - centers[c]).norm(dim=2) < radii[c]).any(1).double() * 2 - 1 for c in range(4)], dim=1)
+    fkk = ns.FKKernelShim(robot.fkine, K.RQKernel(10.0))
+    mdc = ns.legacy_MultiDiffCo.MultiDiffCo(None, kernel_func=fkk, beta=1.0)
+    mdc.train(X, Y, max_iteration=len(X))
+    idx = torch.tensor([int(torch.where((X == sp).all(1))[0][0]) for sp in mdc.support_points])
+    # default rbf kernel MultiQuadratic(1) (deprecated/MultiDiffCo.py:138); Polyharmonic(1) has a zero diagonal and the
+    # block-zeroing of :143-150 makes the system singular on this data
+    mdc.fit_poly(kernel_func=None, target="label", fkine=robot.fkine)
+    Q = torch.rand(20, 7, generator=g, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+    go = torch.randn(20, 4, generator=g, dtype=torch.float64)
+    qv = Q.clone().requires_grad_(True)
+    s = mdc.score(qv)
+    (s * go).sum().backward()
+    gs = qv.grad.clone()
+    qv = Q.clone().requires_grad_(True)
+    r = mdc.rbf_score(qv)
+    (r * go).sum().backward()
+    gr = qv.grad.clone()
+    jac = torch.autograd.functional.jacobian(lambda q: mdc.rbf_score(q).sum(0), Q)  # (C, B, D)
+    np.savez_compressed(os.path.join(OUT, "multiclass.npz"), X=_np(X), Y=_np(Y), idx=_np(idx), gains=_np(mdc.gains),
+                        hyp=_np(mdc.hypothesis), nodes=_np(mdc.rbf_nodes), Q=_np(Q), go=_np(go), score=_np(s),
+                        score_grad=_np(gs), rbf=_np(r), rbf_grad=_np(gr), rbf_jac=_np(jac.permute(1, 0, 2)))
+
+
+def gen_optim_replay(ns):
+    """Run the reference optimisers (diffco/optim.py) with the reference perceptron as ``dist_est`` and record every
+    query it receives with the value and the gradient autograd produced.  The GPU tests replay the queries through the
+    CUDA ``dist_est`` (the optimisers themselves live in /root/reference and do not travel)."""
+    M, K, P, OPT = ns.model, ns.kernel, ns.kernel_perceptrons, ns.optim
+    g = torch.Generator().manual_seed(41)
+    robot = M.RevolutePlanarRobot(1.0, 0.3, dof=7)
+    X = (torch.rand(900, 7, generator=g, dtype=torch.float64) * 2 - 1) * np.pi
+    y = _circle_labels(robot.fkine(X))
+    dc = P.DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+    dc.train(X, y, max_iteration=len(X))
+    dc.fit_poly(K.Polyharmonic(1, 1.0), target="label")
+    idx = torch.tensor([int(torch.where((X == sp).all(1))[0][0]) for sp in dc.support_points])
+    calls = []
+
+    def dist_est(p):
+        out = dc.poly_score(p)
+        calls.append((p.detach().clone(), out.detach().clone()))
+        return out
+
+    start = torch.tensor([-2.0, -0.4, 0.3, -0.2, 0.1, 0.2, -0.1], dtype=torch.float64)
+    target = torch.tensor([1.6, 0.5, -0.3, 0.4, -0.2, 0.1, 0.3], dtype=torch.float64)
+    init = torch.from_numpy(np.linspace(start.numpy(), target.numpy(), 12))
+    opts = {"N_WAYPOINTS": 12, "NUM_RE_TRIALS": 1, "MAXITER": 15, "safety_margin": -0.3, "max_speed": 0.6, "seed": 1234,
+            "history": False, "extra_optimizer_options": {"lr": 0.05}, "init_solution": init.clone()}
+    rec_adam = OPT.adam_traj_optimize(robot, dist_est, start, target, dict(opts))
+    n_adam = len(calls)
+    opts2 = dict(opts)
+    opts2["extra_optimizer_options"] = {"ftol": 1e-4, "disp": False}
+    opts2["MAXITER"] = 6
+    opts2["init_solution"] = init.clone()
+    rec_slsqp = OPT.givengrad_traj_optimize(robot, dist_est, start, target, opts2)
+    # keep a bounded subset of the queries, with autograd gradients of sum(clamp(score - margin, min=0))
+    keep = list(range(0, n_adam, 3))[:6] + list(range(n_adam, len(calls), max(1, (len(calls) - n_adam) // 6)))[:6]
+    out = {"X": _np(X), "y": _np(y), "idx": _np(idx), "gains": _np(dc.gains), "nodes": _np(dc.rbf_nodes),
+           "support_points": _np(dc.support_points), "n_calls": np.array([n_adam, len(calls) - n_adam]),
+           "adam_solution": np.array(rec_adam["solution"]), "adam_cost": np.array(rec_adam["cost"]),
+           "slsqp_solution": np.array(rec_slsqp["solution"]), "slsqp_cost": np.array(rec_slsqp["cost"])}
+    for j, ci in enumerate(keep):
+        p, val = calls[ci]
+        pv = p.clone().requires_grad_(True)
+        sc = dc.poly_score(pv)
+        torch.clamp(sc - opts["safety_margin"], min=0).sum().backward()
+        out[f"call{j}_p"], out[f"call{j}_score"], out[f"call{j}_grad"] = _np(p), _np(val), _np(pv.grad)
+    out["n_kept"] = np.array(len(keep))
+    # the SLSQP constraint Jacobian path: jacobian(vectorize=True) of per-segment sums (optim.py:190-218)
+    p = torch.tensor(rec_adam["solution"], dtype=torch.float64)
+
+    def con(pp):
+        dense = ns.utils.dense_path(pp, opts["max_speed"])
+        cost = -(dc.poly_score(dense[1:-1]) - opts["safety_margin"])
+        cost = torch.clamp_(cost, max=0).reshape(-1)
+        n_seg, n_pt = len(pp) - 1, len(dense) - 2
+        mult = n_pt // n_seg + (1 if n_pt % n_seg else 0)
+        if n_seg * mult - n_pt:
+            cost = torch.cat([cost, torch.zeros(n_seg * mult - n_pt, dtype=cost.dtype)])
+        return cost.reshape(n_seg, -1).sum(dim=1)
+
+    jac = torch.autograd.functional.jacobian(con, p.clone().requires_grad_(True), create_graph=False, strict=False,
+                                             vectorize=True, strategy="reverse-mode")
+    out["con_p"], out["con_val"], out["con_jac"] = _np(p), _np(con(p)), _np(jac)
+    out["safety_margin"], out["max_speed"] = np.array(opts["safety_margin"]), np.array(opts["max_speed"])
+    np.savez_compressed(os.path.join(OUT, "optim_replay.npz"), **out)
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    torch.set_num_threads(4)
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load_legacy()
+    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay):
+        fn(ns)
+        print("wrote", fn.__name__)
+
+
+if __name__ == "__main__":
+    main()
