@@ -88,9 +88,8 @@ PROTOTYPES = {
     "dc_launch_count": (C.c_int64, []),
     "dc_supports_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dc_pack_supports": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
-    "dc_score_workspace_bytes": (C.c_int64, [C.POINTER(FkDesc), C.POINTER(Supports), C.c_int64, C.c_int32]),
     "dc_score_grad": (C.c_int, [C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p, C.c_int64,
-                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+                                C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "dc_kernel_matrix": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_fk_forward": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),

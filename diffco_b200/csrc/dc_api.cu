@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(128) fk_vjp_kernel(const __grid_constant__ dc_
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 static int score_grad_generic(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
-                              int64_t batch, void* score, void* grad, const void* grad_out, int32_t grad_mode,
-                              int num_sms, cudaStream_t stream) {
+                              int64_t batch, void* score, int64_t score_ld, void* grad, int64_t grad_ld,
+                              const void* grad_out, int32_t grad_mode, int num_sms, cudaStream_t stream) {
   LsArgs<T> a;
   a.fk = *fk;
   if (!make_radial_consts<T>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
@@ -196,6 +196,8 @@ static int score_grad_generic(const dc_fk_desc* fk, const dc_kernel_desc* kernel
   a.grad = static_cast<T*>(grad);
   a.grad_out = static_cast<const T*>(grad_out);
   a.batch = batch;
+  a.score_ld = score_ld;
+  a.grad_ld = grad_ld;
   a.n_sv = (int)sv->n;
   a.n_feat = sv->n_features;
   a.n_class = sv->n_class;
@@ -268,15 +270,9 @@ int dc_pack_supports(const void* s_feat, const void* w, int64_t n, int32_t n_fea
   return DC_OK;
 }
 
-int64_t dc_score_workspace_bytes(const dc_fk_desc* fk, const dc_supports* sv, int64_t batch, int32_t grad_mode) {
-  (void)fk; (void)sv; (void)batch; (void)grad_mode;
-  return 0;
-}
-
 int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
-                  int64_t batch, void* score, void* grad, const void* grad_out, int32_t grad_mode, void* workspace,
-                  dc_stream_t stream) {
-  (void)workspace;
+                  int64_t batch, void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out,
+                  int32_t grad_mode, dc_stream_t stream) {
   if (!fk || !kernel || !sv || !fk_valid(*fk)) return DC_ERR_INVALID_ARG;
   if (batch == 0) return DC_OK;
   if (batch < 0 || !q || !score || !sv->table || sv->n < 1 || sv->n > 0x7fffffff) return DC_ERR_INVALID_ARG;
@@ -286,13 +282,18 @@ int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
   int32_t f_pad = 0, row = 0;
   if (dc_supports_layout(sv->n_features, sv->n_class, sv->dtype, &f_pad, &row) != DC_OK) return DC_ERR_INVALID_ARG;
   if (F != sv->n_features || f_pad != sv->f_pad || row != sv->row_stride) return DC_ERR_INVALID_ARG;
+  const int64_t grad_cols = (grad_mode == DC_GRAD_JAC) ? (int64_t)sv->n_class * fk->dof : fk->dof;
+  if (score_ld == 0) score_ld = sv->n_class;
+  if (grad_ld == 0) grad_ld = grad_cols;
+  if (score_ld < sv->n_class || (grad_mode != DC_GRAD_NONE && grad_ld < grad_cols)) return DC_ERR_INVALID_ARG;
   int num_sms = 0;
   const int st = device_sm_count(&num_sms);
   if (st != DC_OK) return st;
   cudaStream_t cs = (cudaStream_t)stream;
 
   if (sv->dtype == DC_F64)
-    return score_grad_generic<double>(fk, kernel, sv, q, batch, score, grad, grad_out, grad_mode, num_sms, cs);
+    return score_grad_generic<double>(fk, kernel, sv, q, batch, score, score_ld, grad, grad_ld, grad_out, grad_mode, num_sms,
+                                      cs);
 
   // fp32: thread-per-query kernel for large batches of the instantiated shapes, lane-split kernel otherwise
   const int kind = fast_radial_kind(*kernel);
@@ -313,6 +314,8 @@ int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
       a.grad = (float*)grad;
       a.grad_out = (const float*)go;
       a.batch = batch;
+      a.score_ld = score_ld;
+      a.grad_ld = grad_ld;
       a.n_sv = (int)sv->n;
       a.n_feat = F;
       a.n_class = C;
@@ -324,7 +327,7 @@ int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
       if (r != DC_ERR_UNSUPPORTED) return r;
     }
   }
-  return score_grad_generic<float>(fk, kernel, sv, q, batch, score, grad, grad_out, grad_mode, num_sms, cs);
+  return score_grad_generic<float>(fk, kernel, sv, q, batch, score, score_ld, grad, grad_ld, grad_out, grad_mode, num_sms, cs);
 }
 
 int dc_kernel_matrix(const dc_kernel_desc* kernel, const void* xa, int64_t na, const void* xb, int64_t nb,

@@ -29,6 +29,8 @@ struct LsArgs {
   T* grad;
   const T* grad_out;
   long long batch;
+  long long score_ld;
+  long long grad_ld;
   int n_sv;
   int n_feat;
   int n_class;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kLsWarps * 32) score_ls_kernel(const __grid_co
       if (pass == 0 && lane < C) {
         T s = (T)0;
         for (int w = 0; w < wpq; ++w) s += part[lead + w][lane];
-        a.score[(size_t)b * C + lane] = s * a.rc.score_scale;
+        a.score[(size_t)b * a.score_ld + lane] = s * a.rc.score_scale;
       }
       if (GRAD) {
         // reduced feature gradient back into part[lead] (lanes stride over features)
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kLsWarps * 32) score_ls_kernel(const __grid_co
         }
         __syncwarp();
         if (lane == 0) {
-          T* out = (a.grad_mode == DC_GRAD_JAC) ? a.grad + ((size_t)b * C + pass) * a.n_in : a.grad + (size_t)b * a.n_in;
+          T* out = a.grad + (size_t)b * a.grad_ld + (a.grad_mode == DC_GRAD_JAC ? (size_t)pass * a.n_in : 0);
           if (a.fk.type == DC_FK_NONE) {
             for (int f = 0; f < F; ++f) out[f] = part[lead][DC_MAX_CLASSES + f];
           } else {

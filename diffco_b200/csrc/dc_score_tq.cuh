@@ -39,6 +39,8 @@ struct ScoreArgs {
   T* grad;
   const T* grad_out;
   long long batch;
+  long long score_ld;  // elements between consecutive rows of score (>= C)
+  long long grad_ld;   // elements between consecutive rows of grad  (>= D, or >= C*D in Jacobian mode)
   int n_sv;
   int n_feat;   // F
   int n_class;  // C
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
         for (int w = 0; w < NW; ++w) s += red[((size_t)w * NRED + kk) * QT + qi];
         if (kk < CW) {
           const long long b = b_base + toff + qi;
-          if (kk < a.n_class && b < a.batch) a.score[(size_t)b * a.n_class + kk] = s * a.rc.score_scale;
+          if (kk < a.n_class && b < a.batch) a.score[(size_t)b * a.score_ld + kk] = s * a.rc.score_scale;
         } else {
           gs[(size_t)(kk - CW) * ST + toff + qi] = s * a.rc.grad_scale;
         }
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
             if (MODE == M_JAC && gi2 >= a.n_class) break;
             T scale = (T)1;
             if (MODE == M_GRAD && CW == 1 && a.grad_out != nullptr) scale = a.grad_out[b];
-            T* out = (MODE == M_JAC) ? a.grad + ((size_t)b * a.n_class + gi2) * a.n_in : a.grad + (size_t)b * a.n_in;
+            T* out = a.grad + (size_t)b * a.grad_ld + (MODE == M_JAC ? (size_t)gi2 * a.n_in : 0);
             for (int f = 0; f < a.n_feat; ++f) out[f] = scale * gs[((size_t)gi2 * F2 + f) * ST + tid];
           }
         } else {
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
             fk_vjp<T>(a.fk, qv, xs + tid, ST, gs + (size_t)gi2 * F2 * ST + tid, ST, gq);
             T scale = (T)1;
             if (MODE == M_GRAD && CW == 1 && a.grad_out != nullptr) scale = a.grad_out[b];
-            T* out = (MODE == M_JAC) ? a.grad + ((size_t)b * a.n_class + gi2) * a.n_in : a.grad + (size_t)b * a.n_in;
+            T* out = a.grad + (size_t)b * a.grad_ld + (MODE == M_JAC ? (size_t)gi2 * a.n_in : 0);
             for (int i = 0; i < a.n_in; ++i) out[i] = scale * gq[i];
           }
         }

@@ -84,10 +84,13 @@ class SupportSet:
 
 
 def score_grad(fk: FkDesc, kernel: KernelDesc, sv: SupportSet, q: torch.Tensor, grad_mode: int = DC_GRAD_NONE,
-               grad_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               grad_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None
+               ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """One launch of the fused hot path.  q: (B, D) on ``sv.device`` with ``sv.dtype``.
 
-    Returns ``score`` (B, C) and, per ``grad_mode``, ``None`` | grad (B, D) | Jacobian (B, C, D).
+    Returns ``score`` (B, C) and, per ``grad_mode``, ``None`` | grad (B, D) | Jacobian (B, C, D).  ``out``: optional
+    preallocated (B, C + D) [DC_GRAD_SUM] / (B, C) [DC_GRAD_NONE] buffer (any row stride) that receives the fused
+    record [score | grad]; the returned tensors are then views into it.
     """
     lib = _lib.load()
     if q.device != sv.device or q.dtype != sv.dtype:
@@ -97,23 +100,34 @@ def score_grad(fk: FkDesc, kernel: KernelDesc, sv: SupportSet, q: torch.Tensor, 
     if fk.n_features != sv.n_features:
         raise ValueError(f"feature map yields {fk.n_features} features, support set has {sv.n_features}")
     q = q.detach().contiguous()
-    B = q.shape[0]
-    score = torch.empty((B, sv.n_class), dtype=sv.dtype, device=sv.device)
+    B, Cn, D = q.shape[0], sv.n_class, fk.dof
     grad = None
-    if grad_mode == DC_GRAD_SUM:
-        grad = torch.empty((B, fk.dof), dtype=sv.dtype, device=sv.device)
-    elif grad_mode == DC_GRAD_JAC:
-        grad = torch.empty((B, sv.n_class, fk.dof), dtype=sv.dtype, device=sv.device)
+    if out is not None:
+        if grad_mode == DC_GRAD_JAC:
+            raise ValueError("out= is not supported with DC_GRAD_JAC")
+        cols = Cn + (D if grad_mode == DC_GRAD_SUM else 0)
+        if out.shape != (B, cols) or out.dtype != sv.dtype or out.device != sv.device or (B > 1 and out.stride(1) != 1):
+            raise ValueError(f"out must be a ({B}, {cols}) {sv.dtype} tensor on {sv.device} with unit column stride")
+        score = out[:, :Cn]
+        grad = out[:, Cn:] if grad_mode == DC_GRAD_SUM else None
+        score_ld = grad_ld = out.stride(0) if B > 1 else cols
+    else:
+        score = torch.empty((B, Cn), dtype=sv.dtype, device=sv.device)
+        if grad_mode == DC_GRAD_SUM:
+            grad = torch.empty((B, D), dtype=sv.dtype, device=sv.device)
+        elif grad_mode == DC_GRAD_JAC:
+            grad = torch.empty((B, Cn, D), dtype=sv.dtype, device=sv.device)
+        score_ld = grad_ld = 0
     go = None
     if grad_out is not None:
         if grad_mode != DC_GRAD_SUM:
             raise ValueError("grad_out is only meaningful with DC_GRAD_SUM")
-        go = grad_out.detach().to(device=sv.device, dtype=sv.dtype).reshape(B, sv.n_class).contiguous()
+        go = grad_out.detach().to(device=sv.device, dtype=sv.dtype).reshape(B, Cn).contiguous()
     if B == 0:
         return score, grad
     with torch.cuda.device(sv.device):
-        st = lib.dc_score_grad(C.byref(fk), C.byref(kernel), C.byref(sv.desc), q.data_ptr(), B, score.data_ptr(),
-                               _ptr(grad), _ptr(go), grad_mode, None, _stream_ptr(sv.device))
+        st = lib.dc_score_grad(C.byref(fk), C.byref(kernel), C.byref(sv.desc), q.data_ptr(), B, score.data_ptr(), score_ld,
+                               _ptr(grad), grad_ld, _ptr(go), grad_mode, _stream_ptr(sv.device))
     _lib.check(st, "dc_score_grad")
     return score, grad
 
@@ -168,7 +182,7 @@ class _ScoreFunction(torch.autograd.Function):
     """score = evaluator(q) with the analytic Jacobian stashed for backward.
 
     ``evaluator(q_dev, want_jac) -> (score (B,C), jac (B,C,D) | None)`` runs the fused CUDA kernel.  backward is
-    ``einsum('bc,bcd->bd')`` — pure torch ops on the stashed Jacobian — so it also works when autograd batches the
+    a multiply + sum over classes — pure torch ops on the stashed Jacobian — so it also works when autograd batches the
     upstream gradient (``torch.autograd.functional.jacobian(vectorize=True)``, diffco/optim.py:211-216).  The
     Jacobian is a constant w.r.t. autograd: second derivatives (optim.py:380-391, trust-constr Hessians) are not
     provided and fail loudly instead of silently returning zeros.
@@ -192,7 +206,8 @@ class _ScoreFunction(torch.autograd.Function):
         (jac,) = ctx.saved_tensors
         if grad_score is None:
             return None, None
-        return torch.einsum("...bc,bcd->...bd", grad_score.to(jac.dtype), jac), None
+        # mul + sum (not einsum / bmm): both have batching rules, which the vmapped backward needs
+        return (grad_score.to(jac.dtype).unsqueeze(-1) * jac).sum(-2), None
 
 
 def differentiable_score(q: torch.Tensor, evaluator) -> torch.Tensor:
@@ -222,3 +237,55 @@ class _FkFunction(torch.autograd.Function):
     def backward(ctx, grad_x):
         (q,) = ctx.saved_tensors
         return ctx.runner.vjp(q, grad_x), None
+
+
+# --------------------------------------------------------------------------------------------------------
+# host buffers in / host buffers out
+# --------------------------------------------------------------------------------------------------------
+
+
+class HostPipeline:
+    """Chunked H2D -> kernel -> D2H pipeline over two side streams with persistent device staging buffers.
+
+    The side streams fork from and join back into the caller's current stream, so events recorded on the current
+    stream bracket all of the work and the call itself never synchronises with the host.
+    """
+
+    def __init__(self, device: torch.device, n_slots: int = 2):
+        self.device = device
+        self.streams = [torch.cuda.Stream(device) for _ in range(n_slots)]
+        self._stage = {}
+
+    def stage(self, name: str, shape, dtype, slot: int) -> torch.Tensor:
+        key = (name, slot)
+        t = self._stage.get(key)
+        if t is None or t.dtype != dtype or t.shape[1:] != tuple(shape[1:]) or t.shape[0] < shape[0]:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._stage[key] = t
+        return t[:shape[0]]
+
+    def run(self, q_host: torch.Tensor, out_host: torch.Tensor, local_fn, record_width: int, chunks: int) -> None:
+        b, d = q_host.shape
+        if out_host.shape != (b, record_width):
+            raise ValueError(f"out_host must have shape ({b}, {record_width}), got {tuple(out_host.shape)}")
+        if b == 0:
+            return
+        chunks = max(1, min(chunks, b))
+        per = -(-b // chunks)
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        for i in range(chunks):
+            lo, hi = i * per, min(b, (i + 1) * per)
+            if hi <= lo:
+                break
+            slot = i % len(self.streams)
+            st = self.streams[slot]
+            with torch.cuda.stream(st):
+                qd = self.stage("q", (per, d), q_host.dtype, slot)[:hi - lo]
+                od = self.stage("o", (per, record_width), out_host.dtype, slot)[:hi - lo]
+                qd.copy_(q_host[lo:hi], non_blocking=True)
+                local_fn(qd, od)
+                out_host[lo:hi].copy_(od, non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)

@@ -139,13 +139,13 @@ int dc_pack_supports(const void* s_feat, const void* w, int64_t n, int32_t n_fea
  * The hot path.  score[B,C] = sum_n w[n,c] k(|FK(q_b) - s_n|^2) and, per grad_mode, its gradient w.r.t. q.
  * fk->type == DC_FK_NONE: q is the feature matrix X[B,F] itself (poly_score(transformed_point=...),
  * kernel_perceptrons.py:316-317) and gradients are w.r.t. X.
- * workspace: optional device scratch of dc_score_workspace_bytes() bytes (needed only when the launch splits the
- * support set across CTAs, i.e. small B); may be NULL when that returns 0.
+ * score_ld / grad_ld: elements between consecutive rows of score / grad; 0 = dense (C, and D or C*D).  Passing the
+ * two halves of one [B, C+D] buffer (score_ld = grad_ld = C+D) makes the launch write the fused record that the
+ * multi-GPU all-gather ships.
  */
-int64_t dc_score_workspace_bytes(const dc_fk_desc* fk, const dc_supports* sv, int64_t batch, int32_t grad_mode);
 int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
-                  int64_t batch, void* score, void* grad, const void* grad_out, int32_t grad_mode, void* workspace,
-                  dc_stream_t stream);
+                  int64_t batch, void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out,
+                  int32_t grad_mode, dc_stream_t stream);
 
 /* K[Na,Nb] = k(|xa_i - xb_j|^2) on pre-transformed features (training rows, fit_poly, jump-start block). */
 int dc_kernel_matrix(const dc_kernel_desc* kernel, const void* xa, int64_t na, const void* xb, int64_t nb,

@@ -1,0 +1,632 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes -> libdiffco_b200.so), against
+
+  * the golden fixtures produced by the unmodified reference (tests/golden/, oracle/make_golden.py),
+  * the float64 oracle (oracle/diffco_oracle.py) on the same seeded inputs at sizes it finishes in seconds,
+  * size-independent properties at BASELINE.json's full sizes (sampled rows vs the oracle, linearity in the
+    weights, position independence / batch-splitting idempotence, Jacobian-vs-VJP consistency).
+
+Gate: max|delta| / max|ref64| <= 1e-5 for float32, 1e-11 for float64; support-vector index
+selection in train() bit-exact against the float64 reference.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import diffco_oracle as O
+from tests import problems as P
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+T64 = lambda a: torch.from_numpy(np.asarray(a)).double()
+TOL = {torch.float32: 1e-5, torch.float64: 1e-11}
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_device):
+    from diffco_b200 import _lib
+
+    _lib.load()  # fails loudly when the CUDA extension is missing
+    return cuda_device
+
+
+def rel(a, b):
+    return P.rel_to_max(torch.as_tensor(a), torch.as_tensor(b))
+
+
+def kernel_pair(name):
+    """(product kernel object, oracle KernelSpec)."""
+    from diffco_b200 import kernel as K
+
+    return {
+        "rq": (K.RQKernel(10.0), O.KernelSpec("rq", 10.0, 2)),
+        "rq3": (K.RQKernel(3.0, 3), O.KernelSpec("rq", 3.0, 3)),
+        "rq1": (K.RQKernel(1.0, 1), O.KernelSpec("rq", 1.0, 1)),
+        "ph1": (K.Polyharmonic(1, 1.0), O.KernelSpec("polyharmonic", 1.0, 1)),
+        "ph1s": (K.Polyharmonic(1, 0.01), O.KernelSpec("polyharmonic", 0.01, 1)),
+        "ph3": (K.Polyharmonic(3, 0.5), O.KernelSpec("polyharmonic", 0.5, 3)),
+        "ph2": (K.Polyharmonic(2, 1.0), O.KernelSpec("polyharmonic", 1.0, 2)),
+        "mq": (K.MultiQuadratic(0.7), O.KernelSpec("multiquadric", 0.7, 0)),
+    }[name]
+
+
+def oracle_score_grad(robot, kspec, S, W, q, go=None):
+    fk = P.oracle_fk(robot)
+    St = fk(S).reshape(len(S), -1)
+    f = lambda z: O.score_original(z, lambda t: fk(t).reshape(len(t), -1), kspec, St, W)
+    s, g = O.score_and_grad(f, q, go)
+    return s.reshape(len(q), -1), g
+
+
+def cuda_support_set(robot, S, W, dtype, dev):
+    """support_transformed is computed by the float64 oracle FK and cast, exactly like the model attributes a user
+    would hand over; the fused kernel then only has to reproduce FK for the queries."""
+    from diffco_b200 import functional as Fn
+
+    St = P.oracle_fk(robot)(S).reshape(len(S), -1)
+    return Fn.SupportSet(St.to(dtype), W.to(dtype), dev)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FK and kernel matrices against the reference's golden vectors
+# ------------------------------------------------------------------------------------------------------------------
+FK_NAMES = ["planar2", "planar3", "planar7", "se2", "se3", "baxter", "baxter_right", "baxter_dual", "panda", "panda5",
+            "dual_panda"]
+F32_ONLY = {"se2", "se3", "baxter_dual"}  # maps the reference itself can only run in float32
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("name", FK_NAMES)
+def test_fk_forward_and_vjp_match_reference(name, dtype, dev):
+    from diffco_b200 import functional as Fn
+
+    g = load("fk.npz")
+    robot = P.make_robot("baxter" if name == "baxter_right" else name)
+    q = T64(g[name + "_q"]).to(device=dev, dtype=dtype)
+    x = Fn.fk_forward(robot.fk_desc, q)
+    tol = 2e-6 if (dtype == torch.float32 or name in F32_ONLY) else 1e-12
+    assert rel(x.reshape(g[name + "_x"].shape), g[name + "_x"]) <= tol
+    gq = Fn.fk_vjp(robot.fk_desc, q, T64(g[name + "_gx"]).to(device=dev, dtype=dtype))
+    assert rel(gq, g[name + "_gq"]) <= max(tol, 1e-7 if name == "baxter_dual" else 1e-11)
+    # the Model.fkine protocol: (B, M, d), differentiable
+    qv = T64(g[name + "_q"]).to(dtype).requires_grad_(True)  # CPU query, like the reference optimisers pass
+    pts = robot.fkine(qv)
+    assert pts.shape == g[name + "_x"].shape and pts.device.type == "cpu"
+    (pts * T64(g[name + "_gx"]).to(dtype)).sum().backward()
+    assert rel(qv.grad, g[name + "_gq"]) <= max(tol, 1e-7 if name == "baxter_dual" else 1e-11)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("name,key", [("rq", "rq_g10_p2"), ("rq3", "rq_g3_p3"), ("rq1", "rq_g1_p1"), ("ph1", "ph_k1_e1"),
+                                      ("ph3", "ph_k3_e05"), ("ph2", "ph_k2_e1"), ("ph1s", "ph_k1_e001"), ("mq", "mq_e07")])
+def test_kernel_matrix_matches_reference(name, key, dtype, dev):
+    g = load("kernels.npz")
+    kfun, _ = kernel_pair(name)
+    x, s = T64(g["x"]).to(device=dev, dtype=dtype), T64(g["s"]).to(device=dev, dtype=dtype)
+    if name == "mq":
+        x, s = x.reshape(5, -1), s.reshape(7, -1)
+    k = kfun(x, s)
+    assert k.shape == g[key].shape
+    assert rel(k, g[key]) <= (2e-6 if dtype == torch.float32 else 1e-12)
+    if key + "_single" in g.files and name != "mq":
+        k1 = kfun(x[0], s)  # kernel.py:18-27 shape quirks: RQ squeezes a single row, Polyharmonic does not
+        assert k1.shape == g[key + "_single"].shape
+        assert rel(k1, g[key + "_single"]) <= (2e-6 if dtype == torch.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("name,key", [("rq", "rq_g10_p2"), ("ph1", "ph_k1_e1"), ("ph3", "ph_k3_e05"), ("mq", "mq_e07")])
+def test_feature_gradient_matches_reference_autograd(name, key, dtype, dev):
+    """d sum(K w)/dx on raw features (transform=None), including the exact r == 0 coincidence in the fixture."""
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    g = load("kernels.npz")
+    kfun, _ = kernel_pair(name)
+    x, s, w = T64(g["x"]).reshape(5, -1), T64(g["s"]).reshape(7, -1), T64(g["w"])
+    sv = Fn.SupportSet(s.to(dtype), w.to(dtype), dev)
+    score, grad = Fn.score_grad(Fn.none_fk(6), kfun.desc, sv, x.to(device=dev, dtype=dtype), _lib.DC_GRAD_SUM)
+    assert rel(score.reshape(-1), (T64(g[key]).reshape(5, 7) @ w)) <= TOL[dtype]
+    assert rel(grad, np.asarray(g[key + "_gradx"]).reshape(5, -1)) <= TOL[dtype]
+    assert torch.isfinite(grad).all()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused score + gradient against the float64 oracle, every FK map x every kernel family, both kernels' paths
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("kname", ["rq", "ph1", "mq"])
+@pytest.mark.parametrize("rname", P.ROBOTS)
+def test_score_grad_matches_oracle_small_batch(rname, kname, dtype, dev):
+    """B = 37 (ragged): the lane-split kernel the optimisers hit."""
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    robot, S, W = P.synthetic_model(rname, 301, 1, seed=100)
+    gen = torch.Generator().manual_seed(101)
+    q = P.sample_configs(robot, 37, gen)
+    q[3] = S[17]  # coincides with a support: r == 0
+    kfun, kspec = kernel_pair(kname)
+    s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q)
+    sv = cuda_support_set(robot, S, W, dtype, dev)
+    s, g = Fn.score_grad(robot.fk_desc, kfun.desc, sv, q.to(device=dev, dtype=dtype), _lib.DC_GRAD_SUM)
+    assert rel(s, s_ref) <= TOL[dtype]
+    assert rel(g, g_ref) <= TOL[dtype]
+    s2, none = Fn.score_grad(robot.fk_desc, kfun.desc, sv, q.to(device=dev, dtype=dtype), _lib.DC_GRAD_NONE)
+    assert none is None and torch.equal(s2, s)
+
+
+@pytest.mark.parametrize("kname", ["rq", "ph1", "mq"])
+@pytest.mark.parametrize("rname", P.ROBOTS)
+def test_score_grad_matches_oracle_large_batch_f32(rname, kname, dev):
+    """B = 4133 (ragged, > the thread-per-query threshold), N = 523 (ragged against the 16 warp slices and the TMA
+    chunking): the persistent TMA kernel where it is instantiated, the lane-split kernel elsewhere."""
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    robot, S, W = P.synthetic_model(rname, 523, 1, seed=200)
+    gen = torch.Generator().manual_seed(201)
+    q = P.sample_configs(robot, 4133, gen)
+    q[4000] = S[5]
+    kfun, kspec = kernel_pair(kname)
+    s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q)
+    sv = cuda_support_set(robot, S, W, torch.float32, dev)
+    qd = q.to(device=dev, dtype=torch.float32)
+    s, g = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd, _lib.DC_GRAD_SUM)
+    assert rel(s, s_ref) <= 1e-5
+    assert rel(g, g_ref) <= 1e-5
+    s2, _ = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd, _lib.DC_GRAD_NONE)
+    assert rel(s2, s_ref) <= 1e-5
+    # upstream gradient folded into the launch
+    go = torch.randn(len(q), 1, generator=gen, dtype=torch.float64)
+    _, g_ref2 = oracle_score_grad(robot, kspec, S, W, q, go)
+    _, g2 = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd, _lib.DC_GRAD_SUM, go.to(dev))
+    assert rel(g2, g_ref2) <= 1e-5
+
+
+@pytest.mark.parametrize("kname", ["rq3", "rq1", "ph3", "ph2", "ph1s"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_generic_kernel_orders(kname, dtype, dev):
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    robot, S, W = P.synthetic_model("planar3", 150, 1, seed=300)
+    q = P.sample_configs(robot, 2300, torch.Generator().manual_seed(301))
+    q[7] = S[3]
+    kfun, kspec = kernel_pair(kname)
+    s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q)
+    sv = cuda_support_set(robot, S, W, dtype, dev)
+    s, g = Fn.score_grad(robot.fk_desc, kfun.desc, sv, q.to(device=dev, dtype=dtype), _lib.DC_GRAD_SUM)
+    assert rel(s, s_ref) <= TOL[dtype]
+    assert rel(g, g_ref) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B", [29, 3000])
+@pytest.mark.parametrize("C", [2, 4, 7])
+@pytest.mark.parametrize("rname,kname", [("baxter", "ph1"), ("planar7", "rq"), ("se2arm", "mq")])
+def test_multiclass_score_grad_and_jacobian(rname, kname, C, B, dtype, dev):
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    robot, S, W = P.synthetic_model(rname, 211, C, seed=400 + C)
+    gen = torch.Generator().manual_seed(401)
+    q = P.sample_configs(robot, B, gen)
+    go = torch.randn(B, C, generator=gen, dtype=torch.float64)
+    kfun, kspec = kernel_pair(kname)
+    s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q, go)
+    sv = cuda_support_set(robot, S, W, dtype, dev)
+    qd = q.to(device=dev, dtype=dtype)
+    s, g = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd, _lib.DC_GRAD_SUM, go.to(dev))
+    assert s.shape == (B, C) and rel(s, s_ref) <= TOL[dtype]
+    assert rel(g, g_ref) <= TOL[dtype]
+    s3, jac = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd, _lib.DC_GRAD_JAC)
+    assert jac.shape == (B, C, robot.dof) and rel(s3, s_ref) <= TOL[dtype]
+    for c in range(C):
+        e = torch.zeros(B, C, dtype=torch.float64)
+        e[:, c] = 1
+        _, gc = oracle_score_grad(robot, kspec, S, W, q, e)
+        assert rel(jac[:, c], gc) <= TOL[dtype]
+    # the VJP is the Jacobian contracted with the upstream gradient
+    assert rel(torch.einsum("bc,bcd->bd", go.to(jac), jac), g_ref) <= 2 * TOL[dtype]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,N", [(0, 10), (1, 1), (1, 2000), (2, 3), (63, 15), (64, 16), (65, 17), (2048, 1), (2049, 31),
+                                 (5000, 33)])
+def test_ragged_and_degenerate_sizes(B, N, dtype, dev):
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    robot, S, W = P.synthetic_model("planar7", N, 1, seed=500 + N)
+    q = P.sample_configs(robot, B, torch.Generator().manual_seed(501))
+    kfun, kspec = kernel_pair("rq")
+    sv = cuda_support_set(robot, S, W, dtype, dev)
+    s, g = Fn.score_grad(robot.fk_desc, kfun.desc, sv, q.to(device=dev, dtype=dtype), _lib.DC_GRAD_SUM)
+    assert s.shape == (B, 1) and g.shape == (B, 7)
+    if B:
+        s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q)
+        assert rel(s, s_ref) <= TOL[dtype] and rel(g, g_ref) <= TOL[dtype]
+
+
+def test_invalid_arguments_return_status_codes(dev):
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    lib = _lib.load()
+    robot, S, W = P.synthetic_model("planar7", 8, 1, seed=1)
+    sv = cuda_support_set(robot, S, W, torch.float32, dev)
+    kfun, _ = kernel_pair("rq")
+    q = torch.zeros(4, 7, device=dev)
+    out = torch.zeros(4, 1, device=dev)
+    call = lambda fk, k, s, qp, b, sp, gp, mode: lib.dc_score_grad(fk, k, s, qp, b, sp, 0, gp, 0, None, mode, None)
+    fk, kd, sd = C.byref(robot.fk_desc), C.byref(kfun.desc), C.byref(sv.desc)
+    assert call(None, kd, sd, q.data_ptr(), 4, out.data_ptr(), None, 0) == -1
+    assert call(fk, kd, sd, None, 4, out.data_ptr(), None, 0) == -1
+    assert call(fk, kd, sd, q.data_ptr(), -1, out.data_ptr(), None, 0) == -1
+    assert call(fk, kd, sd, q.data_ptr(), 4, out.data_ptr(), None, 1) == -1  # gradient requested, no buffer
+    assert call(fk, kd, sd, q.data_ptr(), 4, out.data_ptr(), None, 9) == -1
+    bad = _lib.KernelDesc(_lib.DC_K_POLYHARMONIC, 1, 0.0)  # eps == 0
+    assert call(fk, C.byref(bad), sd, q.data_ptr(), 4, out.data_ptr(), None, 0) == -1
+    other = P.make_robot("baxter")  # 12 features against a 14-feature support table
+    assert call(C.byref(other.fk_desc), kd, sd, q.data_ptr(), 4, out.data_ptr(), None, 0) == -1
+    assert lib.dc_status_string(-1) == b"invalid argument"
+    with pytest.raises(ValueError):
+        Fn.score_grad(robot.fk_desc, kfun.desc, sv, q.double(), 0)  # dtype mismatch is a host-side error
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's object protocol: trained models from the golden fixtures
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,dof", [("p2", 2), ("p7", 7)])
+def test_train_selects_reference_supports_bit_exact(tag, dof, dev):
+    """fit(): float64 training on the device reproduces the reference's support-vector index set exactly."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+
+    g = load("perceptron.npz")
+    robot = P.make_robot(f"planar{dof}")
+    X, y = T64(g[f"{tag}_X"]), T64(g[f"{tag}_y"])
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+    dc.train(X, y, max_iteration=len(X))
+    assert dc.support_index.tolist() == g[f"{tag}_idx"].tolist()
+    assert rel(dc.gains, g[f"{tag}_gains"]) <= 1e-9
+    assert rel(dc.hypothesis, g[f"{tag}_hyp"]) <= 1e-9
+    assert rel(dc.kernel_matrix, g[f"{tag}_K"]) <= 1e-12
+    assert rel(dc.support_transformed, P.oracle_fk(robot)(X[dc.support_index.cpu()])) <= 1e-12
+    # in-code invariant of the reference (kernel_perceptrons.py:196)
+    assert torch.allclose(dc.hypothesis, dc.kernel_matrix @ dc.gains, atol=1e-4)
+    dc.fit_poly(K.Polyharmonic(1, 1.0), target="label")
+    assert rel(dc.rbf_nodes, g[f"{tag}_nodes"]) <= 1e-7
+
+    # scores + autograd gradients on the held-out queries, CPU float64 in -> CPU float64 out like the reference
+    Q = T64(g[f"{tag}_Q"])
+    qv = Q.clone().requires_grad_(True)
+    s = dc.score(qv)
+    assert s.shape == g[f"{tag}_score"].shape and s.device.type == "cpu"
+    s.sum().backward()
+    assert rel(s, g[f"{tag}_score"]) <= 1e-10 and rel(qv.grad, g[f"{tag}_score_grad"]) <= 1e-9
+    qv = Q.clone().requires_grad_(True)
+    p = dc.poly_score(qv)
+    assert p.shape == g[f"{tag}_poly"].shape
+    p.sum().backward()
+    assert rel(p, g[f"{tag}_poly"]) <= 1e-9 and rel(qv.grad, g[f"{tag}_poly_grad"]) <= 1e-8
+    assert dc.score(Q[5]).shape == g[f"{tag}_single_score"].shape == ()
+    assert dc.poly_score(Q[5]).shape == g[f"{tag}_single_poly"].shape == (1, 1)
+    assert rel(dc.score(Q[5]), g[f"{tag}_single_score"]) <= 1e-10
+    with torch.no_grad():
+        assert rel(dc.rbf_score(Q), g[f"{tag}_poly"]) <= 1e-9  # legacy alias
+
+    # the same model in float32 (model dtype decides, kernel_perceptrons.py:313): 1e-5 gate
+    dc32 = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+    dc32.support_points = dc.support_points.float()
+    dc32.support_transformed = dc.support_transformed.float()
+    dc32.gains, dc32.rbf_nodes, dc32.rbf_kernel = dc.gains.float(), dc.rbf_nodes.float(), K.Polyharmonic(1, 1.0)
+    dc32._valid_supports = dc.valid_supports
+    qv = Q.clone().requires_grad_(True)  # float64 query is cast to the model dtype
+    p32 = dc32.poly_score(qv)
+    assert p32.dtype == torch.float32
+    p32.sum().backward()
+    assert rel(p32, g[f"{tag}_poly"]) <= 1e-5 and rel(qv.grad, g[f"{tag}_poly_grad"]) <= 1e-5
+    qv = Q.float().requires_grad_(True)
+    s32 = dc32.score(qv)
+    s32.sum().backward()
+    assert rel(s32, g[f"{tag}_score"]) <= 1e-5 and rel(qv.grad, g[f"{tag}_score_grad"]) <= 1e-5
+
+
+def test_train_float32_rows_select_reference_supports(dev):
+    """Direct-difference float32 kernel rows reproduce the float64 reference's index set."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+
+    g = load("perceptron.npz")
+    robot = P.make_robot("planar7")
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+    dc.train(T64(g["p7_X"]).float(), T64(g["p7_y"]).float(), max_iteration=len(g["p7_X"]))
+    assert dc.support_index.tolist() == g["p7_idx"].tolist()
+    assert rel(dc.gains, g["p7_gains"]) <= 1e-3  # the greedy loop amplifies rounding; the index set is the gate
+
+
+def test_jump_start_update_matches_reference(dev):
+    """update(): jump_start_initialize + warm-started training (kernel_perceptrons.py:222-269)."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+
+    g = load("perceptron.npz")
+    robot = P.make_robot("planar7")
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+    dc.train(T64(g["p7_X"]), T64(g["p7_y"]), max_iteration=len(g["p7_X"]))
+    Xu, yu, exist = T64(g["p7u_X"]), T64(g["p7u_y"]), torch.from_numpy(g["p7u_exist"])
+    gains0, _, K0, h0 = dc._jump_start(Xu.to(dev), exist.to(dev))
+    assert rel(gains0, g["p7u_gains0"]) <= 1e-9 and rel(h0, g["p7u_h0"]) <= 1e-9 and rel(K0, g["p7u_K0"]) <= 1e-12
+    dc.train(Xu, yu, update=True, exist_mask=exist, max_iteration=len(Xu))
+    assert dc.support_index.tolist() == g["p7u_idx"].tolist()
+    assert rel(dc.gains, g["p7u_gains"]) <= 1e-8 and rel(dc.hypothesis, g["p7u_hyp"]) <= 1e-8
+
+
+def test_legacy_multiclass_matches_reference(dev):
+    from diffco_b200 import MultiDiffCo
+    from diffco_b200 import kernel as K
+
+    g = load("multiclass.npz")
+    robot = P.make_robot("baxter")
+    mdc = MultiDiffCo(None, kernel_func=K.FKKernel(robot.fkine, K.RQKernel(10.0)), beta=1.0)
+    X, Y = T64(g["X"]), T64(g["Y"])
+    mdc.train(X, Y, max_iteration=len(X))
+    assert mdc.support_index.tolist() == g["idx"].tolist()
+    assert mdc.num_class == 4
+    assert rel(mdc.gains, g["gains"]) <= 1e-9 and rel(mdc.hypothesis, g["hyp"]) <= 1e-9
+    mdc.fit_poly(kernel_func=None, target="label", fkine=robot.fkine)
+    assert rel(mdc.rbf_nodes, g["nodes"]) <= 1e-7
+    Q, go = T64(g["Q"]), T64(g["go"])
+    qv = Q.clone().requires_grad_(True)
+    s = mdc.score(qv)
+    assert s.shape == (20, 4)
+    (s * go).sum().backward()
+    assert rel(s, g["score"]) <= 1e-10 and rel(qv.grad, g["score_grad"]) <= 1e-9
+    qv = Q.clone().requires_grad_(True)
+    r = mdc.rbf_score(qv)
+    (r * go).sum().backward()
+    assert rel(r, g["rbf"]) <= 1e-8 and rel(qv.grad, g["rbf_grad"]) <= 1e-8
+    jac = torch.autograd.functional.jacobian(lambda q: mdc.rbf_score(q).sum(0), Q, vectorize=True)  # (C, B, D)
+    assert rel(jac.permute(1, 0, 2), g["rbf_jac"]) <= 1e-8
+
+
+def test_optimizer_call_pattern_replay(dev):
+    """The queries the reference's adam_/givengrad_traj_optimize issued (recorded by oracle/make_golden.py), replayed
+    through the CUDA dist_est with the exact autograd usage of optim.py:86-103 and :190-218."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+
+    g = load("optim_replay.npz")
+    robot = P.make_robot("planar7")
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+    dc.train(T64(g["X"]), T64(g["y"]), max_iteration=len(g["X"]))
+    assert dc.support_index.tolist() == g["idx"].tolist()
+    dc.fit_poly(K.Polyharmonic(1, 1.0), target="label")
+    assert rel(dc.rbf_nodes, g["nodes"]) <= 1e-6
+    margin = float(g["safety_margin"])
+    for j in range(int(g["n_kept"])):
+        p = T64(g[f"call{j}_p"]).requires_grad_(True)
+        sc = dc.poly_score(p)
+        assert rel(sc, g[f"call{j}_score"]) <= 1e-8
+        torch.clamp(sc - margin, min=0).sum().backward()  # optim.py:88-101
+        assert rel(p.grad, g[f"call{j}_grad"]) <= 1e-7
+
+    def con(pp):  # optim.py:190-207
+        dense = O.dense_path(pp, float(g["max_speed"]))
+        cost = -(dc.poly_score(dense[1:-1]) - margin)
+        cost = torch.clamp_(cost, max=0).reshape(-1)
+        n_seg, n_pt = len(pp) - 1, len(dense) - 2
+        mult = n_pt // n_seg + (1 if n_pt % n_seg else 0)
+        if n_seg * mult - n_pt:
+            cost = torch.cat([cost, torch.zeros(n_seg * mult - n_pt, dtype=cost.dtype)])
+        return cost.reshape(n_seg, -1).sum(dim=1)
+
+    p = T64(g["con_p"])
+    assert rel(con(p), g["con_val"]) <= 1e-8
+    jac = torch.autograd.functional.jacobian(con, p.clone().requires_grad_(True), create_graph=False, strict=False,
+                                             vectorize=True, strategy="reverse-mode")  # optim.py:211-216
+    assert rel(jac, g["con_jac"]) <= 1e-7
+
+
+def test_second_derivatives_fail_loudly(dev):
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+
+    robot, S, W = P.synthetic_model("planar3", 20, 1, seed=3)
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine)
+    dc.support_points, dc.support_transformed, dc.gains = S, P.oracle_fk(robot)(S), W[:, 0]
+    q = P.sample_configs(robot, 4, torch.Generator().manual_seed(1)).requires_grad_(True)
+    (gq,) = torch.autograd.grad(dc.score(q).sum(), q, create_graph=True)
+    with pytest.raises(RuntimeError):
+        gq.sum().backward()
+
+
+def test_transformed_point_entry(dev):
+    """poly_score(transformed_point=...) (kernel_perceptrons.py:316-317): features in, gradient w.r.t. features."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+
+    robot, S, W = P.synthetic_model("panda", 64, 1, seed=9)
+    fk = P.oracle_fk(robot)
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine)
+    dc.support_points, dc.support_transformed = S, fk(S)
+    dc.rbf_nodes, dc.rbf_kernel = W[:, 0], K.Polyharmonic(1, 1.0)
+    q = P.sample_configs(robot, 9, torch.Generator().manual_seed(2))
+    x = fk(q).requires_grad_(True)
+    out = dc.poly_score(transformed_point=x)
+    out.sum().backward()
+    xr = fk(q).requires_grad_(True)
+    ref = O.poly_score(xr, None, O.KernelSpec("polyharmonic", 1.0, 1), fk(S), W[:, 0])
+    ref.sum().backward()
+    assert out.shape == (9, 1) and rel(out, ref) <= 1e-11 and rel(x.grad, xr.grad) <= 1e-11
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties
+# ------------------------------------------------------------------------------------------------------------------
+def _full_size_checks(rname, kname, N, C, B, dev, seed, n_sample=384):
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    robot, S, W = P.synthetic_model(rname, N, C, seed=seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    q = P.sample_configs(robot, B, gen)
+    kfun, kspec = kernel_pair(kname)
+    sv = cuda_support_set(robot, S, W, torch.float32, dev)
+    qd = q.to(device=dev, dtype=torch.float32)
+    go = torch.randn(B, C, generator=gen, dtype=torch.float64)
+    god = go.to(device=dev, dtype=torch.float32)
+    s, g = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd, _lib.DC_GRAD_SUM, god)
+    assert torch.isfinite(s).all() and torch.isfinite(g).all()
+
+    # (1) sampled rows against the float64 oracle (includes first / last rows: tile and tail handling)
+    idx = torch.cat([torch.tensor([0, 1, B - 2, B - 1]), torch.randint(0, B, (n_sample,), generator=gen)])
+    s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q[idx], go[idx])
+    assert rel(s[idx.to(dev)], s_ref) <= 1e-5
+    assert rel(g[idx.to(dev)], g_ref) <= 1e-5
+
+    # (2) position independence: the same configurations in a different batch (reversed order, and a ragged slice
+    #     starting mid-tile) give bit-identical rows — the reduction order over support vectors is fixed
+    s_r, g_r = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd.flip(0).contiguous(), _lib.DC_GRAD_SUM, god.flip(0).contiguous())
+    assert torch.equal(s_r.flip(0), s) and torch.equal(g_r.flip(0), g)
+    lo, hi = 12345, 12345 + 7001
+    s_p, g_p = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd[lo:hi].contiguous(), _lib.DC_GRAD_SUM, god[lo:hi].contiguous())
+    assert torch.equal(s_p, s[lo:hi]) and torch.equal(g_p, g[lo:hi])
+
+    # (3) linearity in the weights: score(W1 + W2) == score(W1) + score(W2) (to rounding)
+    W2 = torch.randn(N, C, generator=gen, dtype=torch.float64)
+    sv2 = cuda_support_set(robot, S, W2, torch.float32, dev)
+    sv12 = cuda_support_set(robot, S, W + W2, torch.float32, dev)
+    sub = qd[:16384]
+    sa, ga = Fn.score_grad(robot.fk_desc, kfun.desc, sv, sub, _lib.DC_GRAD_SUM, god[:16384])
+    sb, gb = Fn.score_grad(robot.fk_desc, kfun.desc, sv2, sub, _lib.DC_GRAD_SUM, god[:16384])
+    sab, gab = Fn.score_grad(robot.fk_desc, kfun.desc, sv12, sub, _lib.DC_GRAD_SUM, god[:16384])
+    assert rel(sa + sb, sab) <= 1e-5 and rel(ga + gb, gab) <= 1e-5
+
+    # (4) score-only launch agrees with the score of the score+grad launch
+    s_only, _ = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd, _lib.DC_GRAD_NONE)
+    assert rel(s_only, s) <= 1e-6
+    return robot, kfun, sv, qd, s, g
+
+
+@pytest.mark.parametrize("kname", ["rq", "ph1"])
+def test_full_size_cfg2_planar7_2000sv_65536(kname, dev):
+    """BASELINE.json configs[1]: 7-DoF planar arm, FK + RQ / Polyharmonic, 2000 SVs, batch 65536, score+grad."""
+    _full_size_checks("planar7", kname, 2000, 1, 65536, dev, seed=1234)
+
+
+def test_full_size_cfg3_baxter_4class_5000sv_262144(dev):
+    """BASELINE.json configs[2]: Baxter 7-DoF, 4-class MultiDiffCo, 5000 SVs, batch 262144."""
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+
+    robot, kfun, sv, qd, s, g = _full_size_checks("baxter", "ph1", 5000, 4, 262144, dev, seed=1234)
+    # Jacobian mode is consistent with the VJP at full size (sampled slice)
+    sub = qd[100000:108192].contiguous()
+    _, jac = Fn.score_grad(robot.fk_desc, kfun.desc, sv, sub, _lib.DC_GRAD_JAC)
+    _, gsum = Fn.score_grad(robot.fk_desc, kfun.desc, sv, sub, _lib.DC_GRAD_SUM)
+    assert rel(jac.sum(1), gsum) <= 1e-5
+
+
+def test_cfg1_planar2_raw_config_features(dev):
+    """BASELINE.json configs[0]: 2-DoF, RQKernel on raw configurations (no transform), 200 SVs, batch 1024, score only."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+
+    gen = torch.Generator().manual_seed(2021)
+    S = (torch.rand(200, 2, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi
+    q = (torch.rand(1024, 2, generator=gen, dtype=torch.float64) * 2 - 1) * np.pi
+    w = torch.randn(200, generator=gen, dtype=torch.float64)
+    ref = O.score_original(q, None, O.KernelSpec("rq", 10.0, 2), S, w)
+    for dtype in (torch.float32, torch.float64):
+        dc = DiffCo(kernel_func=K.RQKernel(10.0))
+        dc.support_points = dc.support_transformed = S.to(dtype)
+        dc.gains = w.to(dtype)
+        with torch.no_grad():
+            s = dc.score(q.to(dtype))
+        assert s.shape == (1024,) and rel(s, ref) <= TOL[dtype]
+
+
+def test_cfg4_se2_base_arm_adam_waypoints(dev):
+    """BASELINE.json configs[3]: SE(2) base + 3-link arm, 3000 SVs, 256 waypoints, a short Adam loop on the penalty
+    clamp(score - margin, 0) exactly like optim.py:86-127 drives dist_est; the CUDA dist_est and the oracle dist_est
+    must produce the same trajectory ('MultiFourier' does not exist in the reference: MultiQuadratic and Polyharmonic
+    stand in)."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+
+    robot, S, W = P.synthetic_model("se2arm", 3000, 1, seed=1234)
+    fk = P.oracle_fk(robot)
+    St = fk(S)
+    gen = torch.Generator().manual_seed(7)
+    p0 = P.sample_configs(robot, 256, gen)
+    for kname, kfun in (("mq", K.MultiQuadratic(0.7)), ("ph1", K.Polyharmonic(1, 1.0))):
+        _, kspec = kernel_pair(kname)
+        dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine)
+        dc.support_points, dc.support_transformed = S, St
+        dc.rbf_nodes, dc.rbf_kernel = W[:, 0], kfun
+        margin = float(O.poly_score(p0, fk, kspec, St, W[:, 0]).median())
+        paths = []
+        for dist_est in (dc.poly_score, lambda z: O.poly_score(z, fk, kspec, St, W[:, 0])):
+            p = p0.clone().requires_grad_(True)
+            opt = torch.optim.Adam([p], lr=0.05)
+            for _ in range(12):
+                opt.zero_grad()
+                loss = torch.clamp(dist_est(p) - margin, min=0).sum()
+                loss.backward()
+                p.grad[[0, -1]] = 0.0
+                opt.step()
+            paths.append(p.detach().clone())
+        assert rel(paths[0], paths[1]) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused [score | grad] records, host-buffer pipeline, single-rank ShardedScorer
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [50, 6000])
+def test_fused_record_output_and_host_pipeline(B, dev):
+    from diffco_b200 import DiffCo, _lib
+    from diffco_b200 import distributed as D
+    from diffco_b200 import functional as Fn
+    from diffco_b200 import kernel as K
+
+    robot, S, W = P.synthetic_model("planar7", 400, 1, seed=900)
+    q = P.sample_configs(robot, B, torch.Generator().manual_seed(901))
+    kfun, kspec = kernel_pair("rq")
+    s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q)
+    sv = cuda_support_set(robot, S, W, torch.float32, dev)
+    qd = q.to(device=dev, dtype=torch.float32)
+    big = torch.full((B, 12), -7.0, device=dev)  # record embedded in a wider buffer: row stride 12
+    s, g = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd, _lib.DC_GRAD_SUM, out=big[:, 2:10])
+    assert s.data_ptr() == big[:, 2:3].data_ptr()
+    assert rel(big[:, 2:3], s_ref) <= 1e-5 and rel(big[:, 3:10], g_ref) <= 1e-5
+    assert (big[:, :2] == -7.0).all() and (big[:, 10:] == -7.0).all()  # nothing outside the record was touched
+
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine)
+    dc.support_points, dc.support_transformed, dc.gains = S.float(), P.oracle_fk(robot)(S).float(), W[:, 0].float()
+    scorer = D.ShardedScorer(dc, weights="gains")
+    s1, g1 = scorer.score_and_grad(qd)
+    assert rel(s1, s_ref) <= 1e-5 and rel(g1, g_ref) <= 1e-5
+    s2, g2 = scorer.score_and_grad_global(qd)
+    assert torch.equal(s2, s1) and torch.equal(g2, g1)
+    qh = q.float().pin_memory()
+    oh = torch.empty(B, 8).pin_memory()
+    scorer.score_and_grad_host(qh, oh, chunks=3)
+    torch.cuda.synchronize()
+    assert rel(oh[:, :1], s_ref) <= 1e-5 and rel(oh[:, 1:], g_ref) <= 1e-5
+    # DiffCo.score_and_grad: CPU in, CPU out
+    s3, g3 = dc.score_and_grad(q.float())
+    assert s3.device.type == "cpu" and rel(s3, s_ref) <= 1e-5 and rel(g3, g_ref) <= 1e-5
