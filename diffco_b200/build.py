@@ -23,8 +23,7 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", CSRC] + ARCH_FLAGS
 
 TQ_KINDS = {"rq2": "KR_RQ2", "ph1": "KR_PH1", "mq": "KR_MQ"}
-TQ_VARIANTS = [("c1_score", 1, "M_SCORE"), ("c1_grad", 1, "M_GRAD"), ("c4_score", 4, "M_SCORE"),
-               ("c4_grad", 4, "M_GRAD"), ("c4_jac", 4, "M_JAC")]
+TQ_VARIANTS = [("c1_score", 1, "M_SCORE"), ("c1_grad", 1, "M_GRAD"), ("c4_score", 4, "M_SCORE"), ("c4_grad", 4, "M_GRAD")]
 
 
 def _units():

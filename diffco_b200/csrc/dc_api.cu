@@ -12,22 +12,19 @@ namespace dc {
 
 long long g_launch_count = 0;
 
-#define DC_TQ_DECL(name) int name(int fp, ScoreArgs<float>& a, int num_sms, cudaStream_t stream);
+#define DC_TQ_DECL(name) int name(int n_feat, ScoreArgs<float>& a, int num_sms, cudaStream_t stream);
 DC_TQ_DECL(tq_rq2_c1_score)
 DC_TQ_DECL(tq_rq2_c1_grad)
 DC_TQ_DECL(tq_rq2_c4_score)
 DC_TQ_DECL(tq_rq2_c4_grad)
-DC_TQ_DECL(tq_rq2_c4_jac)
 DC_TQ_DECL(tq_ph1_c1_score)
 DC_TQ_DECL(tq_ph1_c1_grad)
 DC_TQ_DECL(tq_ph1_c4_score)
 DC_TQ_DECL(tq_ph1_c4_grad)
-DC_TQ_DECL(tq_ph1_c4_jac)
 DC_TQ_DECL(tq_mq_c1_score)
 DC_TQ_DECL(tq_mq_c1_grad)
 DC_TQ_DECL(tq_mq_c4_score)
 DC_TQ_DECL(tq_mq_c4_grad)
-DC_TQ_DECL(tq_mq_c4_jac)
 #undef DC_TQ_DECL
 
 int ls_launch_f32(LsArgs<float>& a, int num_sms, cudaStream_t stream);
@@ -37,10 +34,10 @@ static int ls_launch(LsArgs<double>& a, int num_sms, cudaStream_t stream) { retu
 
 typedef int (*tq_fn)(int, ScoreArgs<float>&, int, cudaStream_t);
 // [kind][cw4][mode]
-static tq_fn const kTqTable[3][2][3] = {
-    {{tq_rq2_c1_score, tq_rq2_c1_grad, nullptr}, {tq_rq2_c4_score, tq_rq2_c4_grad, tq_rq2_c4_jac}},
-    {{tq_ph1_c1_score, tq_ph1_c1_grad, nullptr}, {tq_ph1_c4_score, tq_ph1_c4_grad, tq_ph1_c4_jac}},
-    {{tq_mq_c1_score, tq_mq_c1_grad, nullptr}, {tq_mq_c4_score, tq_mq_c4_grad, tq_mq_c4_jac}},
+static tq_fn const kTqTable[3][2][2] = {
+    {{tq_rq2_c1_score, tq_rq2_c1_grad}, {tq_rq2_c4_score, tq_rq2_c4_grad}},
+    {{tq_ph1_c1_score, tq_ph1_c1_grad}, {tq_ph1_c4_score, tq_ph1_c4_grad}},
+    {{tq_mq_c1_score, tq_mq_c1_grad}, {tq_mq_c4_score, tq_mq_c4_grad}},
 };
 
 static int device_sm_count(int* out) {
@@ -209,15 +206,6 @@ static int score_grad_generic(const dc_fk_desc* fk, const dc_kernel_desc* kernel
   return ls_launch(a, num_sms, stream);
 }
 
-static bool tq_fp_available(int fp) {
-  switch (fp) {
-    case 1: case 2: case 3: case 4: case 6: case 7: case 8: case 11: case 12:
-      return true;
-    default:
-      return false;
-  }
-}
-
 // Batches below this go to the lane-split kernel (too few 64-query tiles to occupy the SMs).
 static constexpr int64_t kTqMinBatch = 2048;
 
@@ -246,8 +234,10 @@ int dc_supports_layout(int32_t n_features, int32_t n_class, int32_t dtype, int32
   if (n_features < 1 || n_features > DC_MAX_FEATURES || n_class < 1 || n_class > DC_MAX_CLASSES) return DC_ERR_INVALID_ARG;
   if (dtype != DC_F32 && dtype != DC_F64) return DC_ERR_INVALID_ARG;
   const int fp = 2 * ceil_div(n_features, 2);
+  // classes are padded to the width the thread-per-query kernel is instantiated for (1 or 4) with zero weights
+  const int cp = (n_class == 1) ? 1 : round_up(n_class, 4);
   if (f_pad) *f_pad = fp;
-  if (row_stride) *row_stride = round_up(fp + n_class, 4);
+  if (row_stride) *row_stride = round_up(fp + cp, 4);
   return DC_OK;
 }
 
@@ -297,35 +287,43 @@ int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
 
   // fp32: thread-per-query kernel for large batches of the instantiated shapes, lane-split kernel otherwise
   const int kind = fast_radial_kind(*kernel);
-  const int fp = f_pad / 2;
   const int C = sv->n_class;
-  int mode = grad_mode == DC_GRAD_NONE ? M_SCORE : (grad_mode == DC_GRAD_SUM ? M_GRAD : M_JAC);
-  if (C == 1 && mode == M_JAC) mode = M_GRAD;  // one class: the Jacobian is the unit-upstream gradient
-  const void* go = (grad_mode == DC_GRAD_JAC) ? nullptr : grad_out;
-  if (kind != KR_GENERIC && C <= 4 && tq_fp_available(fp) && batch >= kTqMinBatch) {
-    tq_fn fn = kTqTable[kind][C == 1 ? 0 : 1][mode];
-    if (fn) {
-      ScoreArgs<float> a;
-      a.fk = *fk;
-      if (!make_radial_consts<float>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
-      a.table = (const float*)sv->table;
-      a.q = (const float*)q;
-      a.score = (float*)score;
-      a.grad = (float*)grad;
-      a.grad_out = (const float*)go;
-      a.batch = batch;
-      a.score_ld = score_ld;
-      a.grad_ld = grad_ld;
-      a.n_sv = (int)sv->n;
-      a.n_feat = F;
-      a.n_class = C;
-      a.n_in = fk->dof;
-      a.n_tiles = 0;
-      a.st_q = 0;
-      a.chunk_rows = 0;
-      const int r = fn(fp, a, num_sms, cs);
-      if (r != DC_ERR_UNSUPPORTED) return r;
+  if (kind != KR_GENERIC && C <= 4 && batch >= kTqMinBatch) {
+    tq_fn fn = kTqTable[kind][C == 1 ? 0 : 1][grad_mode == DC_GRAD_NONE ? M_SCORE : M_GRAD];
+    ScoreArgs<float> a;
+    a.fk = *fk;
+    if (!make_radial_consts<float>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
+    a.table = (const float*)sv->table;
+    a.q = (const float*)q;
+    a.score = (float*)score;
+    a.grad = (float*)grad;
+    a.grad_out = (grad_mode == DC_GRAD_SUM) ? (const float*)grad_out : nullptr;
+    a.batch = batch;
+    a.score_ld = score_ld;
+    a.grad_ld = grad_ld;
+    a.n_sv = (int)sv->n;
+    a.n_feat = F;
+    a.n_class = C;
+    a.n_in = fk->dof;
+    a.jac_class = -1;
+    a.write_score = 1;
+    a.n_tiles = 0;
+    a.st_q = 0;
+    a.chunk_rows = 0;
+    int r;
+    if (grad_mode == DC_GRAD_JAC && C > 1) {
+      // Jacobian at large batch: one gradient pass per class (one-hot upstream gradient); the first pass writes the
+      // scores.  The optimisers' Jacobian calls are small-batch and take the lane-split kernel instead.
+      r = DC_OK;
+      for (int c = 0; c < C && r == DC_OK; ++c) {
+        a.jac_class = c;
+        a.write_score = (c == 0);
+        r = fn(F, a, num_sms, cs);
+      }
+    } else {
+      r = fn(F, a, num_sms, cs);
     }
+    if (r != DC_ERR_UNSUPPORTED) return r;
   }
   return score_grad_generic<float>(fk, kernel, sv, q, batch, score, score_ld, grad, grad_ld, grad_out, grad_mode, num_sms, cs);
 }

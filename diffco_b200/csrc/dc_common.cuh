@@ -37,37 +37,27 @@ __host__ __device__ constexpr int round_up(int a, int b) { return ceil_div(a, b)
 
 // ----------------------------------------------------------------------------------------------
 // Packed pairs.  fp32 pairs map onto Blackwell's 2-wide FP32 instructions (FADD2/FMUL2/FFMA2 in SASS,
-// add/mul/fma.f32x2 in PTX): one issue slot, two lanes of work.  fp64 pairs are two scalars.
+// add/mul/fma.f32x2 in PTX): one issue slot, two lanes of work.  The *_b forms take a scalar that the
+// instruction broadcasts to both halves (SASS operand Rx.F32).  Measured on B200 (tools/ubench/fma_pipes.cu):
+// a loop of packed ops alone sustains ~124 of the 128 lane-FMAs/clk/SM, scalar FFMA alone ~119, but a MIX of
+// packed and scalar FMA-pipe instructions drops to ~103 — so the inner loops keep everything packed.
 // ----------------------------------------------------------------------------------------------
-template <typename T>
-struct Pair;
-
-template <>
-struct Pair<float> {
+struct P2 {
   float2 v;
-  __device__ __forceinline__ Pair() {}
-  __device__ __forceinline__ Pair(float a, float b) : v(make_float2(a, b)) {}
-  __device__ __forceinline__ explicit Pair(float2 f) : v(f) {}
+  __device__ __forceinline__ P2() {}
+  __device__ __forceinline__ P2(float a, float b) : v(make_float2(a, b)) {}
+  __device__ __forceinline__ explicit P2(float2 f) : v(f) {}
   __device__ __forceinline__ float lo() const { return v.x; }
   __device__ __forceinline__ float hi() const { return v.y; }
 };
-
-template <>
-struct Pair<double> {
-  double a, b;
-  __device__ __forceinline__ Pair() {}
-  __device__ __forceinline__ Pair(double x, double y) : a(x), b(y) {}
-  __device__ __forceinline__ double lo() const { return a; }
-  __device__ __forceinline__ double hi() const { return b; }
-};
-
-__device__ __forceinline__ Pair<float> padd(Pair<float> x, Pair<float> y) { return Pair<float>(__fadd2_rn(x.v, y.v)); }
-__device__ __forceinline__ Pair<float> pfma(Pair<float> x, Pair<float> y, Pair<float> z) {
-  return Pair<float>(__ffma2_rn(x.v, y.v, z.v));
-}
-__device__ __forceinline__ Pair<double> padd(Pair<double> x, Pair<double> y) { return Pair<double>(x.a + y.a, x.b + y.b); }
-__device__ __forceinline__ Pair<double> pfma(Pair<double> x, Pair<double> y, Pair<double> z) {
-  return Pair<double>(fma(x.a, y.a, z.a), fma(x.b, y.b, z.b));
+__device__ __forceinline__ P2 padd(P2 x, P2 y) { return P2(__fadd2_rn(x.v, y.v)); }
+__device__ __forceinline__ P2 pmul(P2 x, P2 y) { return P2(__fmul2_rn(x.v, y.v)); }
+__device__ __forceinline__ P2 pfma(P2 x, P2 y, P2 z) { return P2(__ffma2_rn(x.v, y.v, z.v)); }
+__device__ __forceinline__ P2 padd_b(P2 x, float s) { return P2(__fadd2_rn(x.v, make_float2(s, s))); }
+__device__ __forceinline__ P2 pmul_b(P2 x, float s) { return P2(__fmul2_rn(x.v, make_float2(s, s))); }
+__device__ __forceinline__ P2 pfma_b(float s, P2 y, P2 z) { return P2(__ffma2_rn(make_float2(s, s), y.v, z.v)); }
+__device__ __forceinline__ P2 pfma_bb(P2 x, float s, float t) {  // x * s + t
+  return P2(__ffma2_rn(x.v, make_float2(s, s), make_float2(t, t)));
 }
 
 // ----------------------------------------------------------------------------------------------

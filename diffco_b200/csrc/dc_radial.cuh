@@ -121,4 +121,26 @@ __device__ __forceinline__ void radial_eval(const RadialConsts<T>& rc, T rho, T&
   }
 }
 
+// Packed form for the thread-per-query kernel: both halves of the pair are different QUERIES against the same support
+// vector, so every step stays a 2-wide instruction (MUFU is scalar and runs on its own pipe).
+template <int KIND>
+__device__ __forceinline__ void radial_eval2(const RadialConsts<float>& rc, P2 rho, P2& k, P2& coef) {
+  if constexpr (KIND == KR_RQ2) {
+    const P2 t = pfma_bb(rho, rc.c0, 1.0f);
+    const P2 u(fast_rcp(t.lo()), fast_rcp(t.hi()));
+    k = pmul(u, u);
+    coef = pmul(k, u);
+  } else if constexpr (KIND == KR_PH1) {
+    const P2 ri(fast_rsqrt(fmaxf(rho.lo(), Tiny<float>::v)), fast_rsqrt(fmaxf(rho.hi(), Tiny<float>::v)));
+    k = pmul(rho, ri);
+    coef = ri;
+  } else {
+    static_assert(KIND == KR_MQ, "thread-per-query kernel: RQ(p=2), Polyharmonic(1) and MultiQuadratic only");
+    const P2 t = pfma_bb(rho, rc.c0, 1.0f);
+    const P2 ri(fast_rsqrt(t.lo()), fast_rsqrt(t.hi()));
+    k = pmul(t, ri);
+    coef = ri;
+  }
+}
+
 }  // namespace dc

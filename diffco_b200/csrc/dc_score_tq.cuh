@@ -6,19 +6,22 @@
 // fkine -> torch.cdist -> pow/reciprocal -> matmul and the autograd backward of all of them
 // (diffco/kernel_perceptrons.py:309-319,362-370; diffco/kernel.py:17-79; diffco/model.py:40-48,225-241).
 //
-// Work decomposition (B200: 148 SMs, one persistent 16-warp CTA per SM):
-//   * the batch is cut into tiles of QT = 32*Q queries; CTA i owns a contiguous, balanced range of tiles;
-//   * tiles are staged in super-tiles of up to NT queries: phase A runs FK one-query-per-thread into shared
-//     memory (xs[F][ST], conflict-free columns), phase C runs the J^T product the same way;
-//   * phase B, per tile: lane l of EVERY warp holds the same Q queries in registers, and the NW warps split the
-//     support set into NW contiguous slices, so all 16 warps stay busy on any batch size that fills the SMs and
-//     the tail quantises at 32*Q queries instead of 512;
+// Work decomposition (B200: 148 SMs, one persistent NW-warp CTA per SM):
+//   * the batch is cut into tiles of QT = 64 queries; CTA i owns a contiguous, balanced range of tiles;
+//   * tiles are staged in super-tiles of up to NT = 32*NW queries: phase A runs FK one-query-per-thread into
+//     shared memory (xs[F][ST], conflict-free columns), phase C runs the J^T product the same way;
+//   * phase B, per tile: lane l of EVERY warp holds queries (2l, 2l+1) of the tile as the two halves of packed
+//     registers, and the NW warps split the support set into NW contiguous slices, so all warps stay busy on any
+//     batch that fills the SMs and the tail quantises at 64 queries;
 //   * each warp streams its own slice of the packed support table HBM/L2 -> shared memory with 1-D bulk TMA
 //     (cp.async.bulk + mbarrier complete_tx) through a private STAGES-deep ring, running STAGES chunks ahead and
 //     prefetching across tile boundaries; rows are read back as warp-uniform LDS.128 broadcasts;
-//   * the pair update is 2-wide packed FP32 (FADD2/FFMA2): per support vector and query FP subtracts, FP fused
-//     squares, one MUFU, ~6 scalar ops, FP fused gradient accumulations;
-//   * partials are combined across warps through shared memory in a fixed order (deterministic results).
+//   * the pair update is 2-wide packed FP32 throughout (FADD2 / FMUL2 / FFMA2 with the support value or weight as
+//     the broadcast scalar operand): per support vector and query pair F subtracts, F fused squares, ~6 packed ops
+//     for the radial profile and the score, 2 MUFU, F fused gradient accumulations — no scalar FMA-pipe
+//     instructions in the loop (mixing them with packed ones costs ~20% of the pipe, tools/ubench/fma_pipes.cu);
+//   * partials are combined across warps through shared memory in a fixed order (deterministic results, and a row's
+//     result does not depend on its position in the batch).
 #pragma once
 
 #include "dc_common.cuh"
@@ -27,7 +30,7 @@
 
 namespace dc {
 
-enum ScoreMode { M_SCORE = 0, M_GRAD = 1, M_JAC = 2 };
+enum ScoreMode { M_SCORE = 0, M_GRAD = 1 };
 
 template <typename T>
 struct ScoreArgs {
@@ -42,35 +45,36 @@ struct ScoreArgs {
   long long score_ld;  // elements between consecutive rows of score (>= C)
   long long grad_ld;   // elements between consecutive rows of grad  (>= D, or >= C*D in Jacobian mode)
   int n_sv;
-  int n_feat;   // F
-  int n_class;  // C
-  int n_in;     // columns of q (dof, or F when fk.type == NONE)
-  int n_tiles;  // ceil(batch / QT)
-  int st_q;     // super-tile size in queries (multiple of QT, <= NT)
+  int n_feat;     // F
+  int n_class;    // C
+  int n_in;       // columns of q (dof, or F when fk.type == NONE)
+  int jac_class;  // >= 0: gradient of class jac_class alone, written at grad + b*grad_ld + jac_class*n_in (Jacobian pass)
+  int write_score;
+  int n_tiles;    // ceil(batch / QT)
+  int st_q;       // super-tile size in queries (multiple of QT, <= NT)
   int chunk_rows;
 };
 
-template <int FP, int CW, int MODE, int Q, int NW, int STAGES>
+template <int F, int CW, int MODE, int NW, int STAGES>
 struct TqCfg {
-  static constexpr int F2 = 2 * FP;
-  static constexpr int ROW = round_up(F2 + CW, 4);
-  static constexpr int QT = 32 * Q;
+  static constexpr int FPAD = round_up(F, 2);
+  static constexpr int ROW = round_up(FPAD + CW, 4);
+  static constexpr int QT = 64;
   static constexpr int NT = 32 * NW;
-  static constexpr int NG = (MODE == M_JAC) ? CW : (MODE == M_GRAD ? 1 : 0);
-  static constexpr int NRED = CW + NG * F2;
+  static constexpr int NG = (MODE == M_GRAD) ? 1 : 0;
+  static constexpr int NRED = CW + NG * F;
   static constexpr int BAR_BYTES = round_up(NW * STAGES * 8, 128);
   __host__ __device__ static constexpr size_t smem_bytes(int st_q, int chunk_rows) {
     return (size_t)BAR_BYTES + sizeof(float) * ((size_t)NW * STAGES * chunk_rows * ROW + (size_t)NW * NRED * QT +
-                                                (size_t)F2 * st_q + (size_t)NG * F2 * st_q);
+                                                (size_t)F * st_q + (size_t)NG * F * st_q);
   }
 };
 
-template <int FP, int KIND, int CW, int MODE, int Q, int NW, int STAGES>
+template <int F, int KIND, int CW, int MODE, int NW, int STAGES>
 __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_constant__ ScoreArgs<float> a) {
   using T = float;
-  using Cfg = TqCfg<FP, CW, MODE, Q, NW, STAGES>;
-  constexpr int F2 = Cfg::F2, ROW = Cfg::ROW, QT = Cfg::QT, NT = Cfg::NT, NG = Cfg::NG, NRED = Cfg::NRED;
-  using P = Pair<T>;
+  using Cfg = TqCfg<F, CW, MODE, NW, STAGES>;
+  constexpr int FPAD = Cfg::FPAD, ROW = Cfg::ROW, QT = Cfg::QT, NT = Cfg::NT, NG = Cfg::NG, NRED = Cfg::NRED;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
   T* ring = ring_all + (size_t)warp * STAGES * CH * ROW;
   T* red = ring_all + (size_t)NW * STAGES * CH * ROW;
   T* xs = red + (size_t)NW * NRED * QT;
-  T* gs = xs + (size_t)F2 * ST;
+  T* gs = xs + (size_t)F * ST;
 
   // ---- this CTA's tiles and this warp's slice of the support set ---------------------------------
   const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
@@ -123,16 +127,17 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
       if (tid < nq) {
         const T* qp = a.q + (size_t)(b_base + tid) * a.n_in;
         if (a.fk.type == DC_FK_NONE) {
-          for (int f = 0; f < a.n_feat; ++f) xs[(size_t)f * ST + tid] = qp[f];
+#pragma unroll
+          for (int f = 0; f < F; ++f) xs[(size_t)f * ST + tid] = qp[f];
         } else {
           T qv[DC_MAX_DOF];
 #pragma unroll
           for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < a.n_in) ? qp[i] : (T)0;
           fk_forward<T>(a.fk, qv, xs + tid, ST);
         }
-        for (int f = a.n_feat; f < F2; ++f) xs[(size_t)f * ST + tid] = (T)0;
       } else {
-        for (int f = 0; f < F2; ++f) xs[(size_t)f * ST + tid] = (T)0;
+#pragma unroll
+        for (int f = 0; f < F; ++f) xs[(size_t)f * ST + tid] = (T)0;
       }
     }
     __syncthreads();
@@ -140,29 +145,33 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
     // ---- phase B: tiles ---------------------------------------------------------------------------
     for (int tl = 0; tl < nt; ++tl) {
       const int toff = tl * QT;
-      P x[Q][FP];
-      T sc[Q][CW];
-      P g[Q][NG > 0 ? NG : 1][FP];
-      T go[Q][CW];
+      P2 x[F];
+      P2 sc[CW];
+      P2 g[NG > 0 ? F : 1];
+      P2 go[CW];
 #pragma unroll
-      for (int j = 0; j < Q; ++j) {
+      for (int f = 0; f < F; ++f) x[f] = P2(*reinterpret_cast<const float2*>(xs + (size_t)f * ST + toff + 2 * lane));
 #pragma unroll
-        for (int p = 0; p < FP; ++p)
-          x[j][p] = P(xs[(size_t)(2 * p) * ST + toff + lane + 32 * j], xs[(size_t)(2 * p + 1) * ST + toff + lane + 32 * j]);
+      for (int c = 0; c < CW; ++c) {
+        sc[c] = P2(0.f, 0.f);
+        go[c] = P2(1.f, 1.f);
+      }
 #pragma unroll
-        for (int c = 0; c < CW; ++c) {
-          sc[j][c] = (T)0;
-          go[j][c] = (T)1;
-        }
+      for (int f = 0; f < (NG > 0 ? F : 1); ++f) g[f] = P2(0.f, 0.f);
+      if constexpr (MODE == M_GRAD && CW > 1) {
+        if (a.jac_class >= 0) {
 #pragma unroll
-        for (int gi2 = 0; gi2 < (NG > 0 ? NG : 1); ++gi2)
+          for (int c = 0; c < CW; ++c) go[c] = (c == a.jac_class) ? P2(1.f, 1.f) : P2(0.f, 0.f);
+        } else {
+          const long long b = b_base + toff + 2 * lane;
 #pragma unroll
-          for (int p = 0; p < FP; ++p) g[j][gi2][p] = P((T)0, (T)0);
-        if constexpr (MODE == M_GRAD && CW > 1) {
-          const long long b = b_base + toff + lane + 32 * j;
-          if (a.grad_out != nullptr && b < a.batch) {
-#pragma unroll
-            for (int c = 0; c < CW; ++c) go[j][c] = (c < a.n_class) ? a.grad_out[(size_t)b * a.n_class + c] : (T)0;
+          for (int c = 0; c < CW; ++c) {
+            T v0 = (c < a.n_class) ? (T)1 : (T)0, v1 = v0;
+            if (a.grad_out != nullptr && c < a.n_class) {
+              v0 = (b < a.batch) ? a.grad_out[(size_t)b * a.n_class + c] : (T)0;
+              v1 = (b + 1 < a.batch) ? a.grad_out[(size_t)(b + 1) * a.n_class + c] : (T)0;
+            }
+            go[c] = P2(v0, v1);
           }
         }
       }
@@ -185,52 +194,41 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
             rowv[4 * i + 2] = v.z;
             rowv[4 * i + 3] = v.w;
           }
+          P2 d[F];
 #pragma unroll
-          for (int j = 0; j < Q; ++j) {
-            P d[FP];
-            P acc0((T)0, (T)0), acc1((T)0, (T)0);
+          for (int f = 0; f < F; ++f) d[f] = padd_b(x[f], rowv[f]);  // the table holds -s
+          P2 acc0 = pmul(d[0], d[0]);
+          P2 acc1(0.f, 0.f);
 #pragma unroll
-            for (int p = 0; p < FP; ++p) d[p] = padd(x[j][p], P(rowv[2 * p], rowv[2 * p + 1]));  // table holds -s
+          for (int f = 1; f < F; ++f) {
+            if (f & 1)
+              acc1 = (f == 1) ? pmul(d[f], d[f]) : pfma(d[f], d[f], acc1);
+            else
+              acc0 = pfma(d[f], d[f], acc0);
+          }
+          if constexpr (F > 1) acc0 = padd(acc0, acc1);
+          P2 k, coef;
+          radial_eval2<KIND>(a.rc, acc0, k, coef);
+          if constexpr (CW == 1) {
+            const T w = rowv[FPAD];
+            sc[0] = pfma_b(w, k, sc[0]);
+            if constexpr (MODE == M_GRAD) {
+              const P2 cc = pmul_b(coef, w);
 #pragma unroll
-            for (int p = 0; p < FP; ++p) {
-              if (p & 1)
-                acc1 = pfma(d[p], d[p], acc1);
-              else
-                acc0 = pfma(d[p], d[p], acc0);
+              for (int f = 0; f < F; ++f) g[f] = pfma(cc, d[f], g[f]);
             }
-            if constexpr (FP > 1) acc0 = padd(acc0, acc1);
-            const T rho = acc0.lo() + acc0.hi();
-            T k, coef;
-            radial_eval<KIND, T>(a.rc, rho, k, coef);
-            if constexpr (CW == 1) {
-              const T w = rowv[F2];
-              sc[j][0] = fma(w, k, sc[j][0]);
-              if constexpr (MODE != M_SCORE) {
-                const T c = w * coef;
-                const P cc(c, c);
+          } else {
+            P2 om(0.f, 0.f);
 #pragma unroll
-                for (int p = 0; p < FP; ++p) g[j][0][p] = pfma(cc, d[p], g[j][0][p]);
-              }
-            } else {
-              T om = (T)0;
+            for (int c = 0; c < CW; ++c) {
+              const T w = rowv[FPAD + c];
+              sc[c] = pfma_b(w, k, sc[c]);
+              if constexpr (MODE == M_GRAD) om = pfma_b(w, go[c], om);
+            }
+            if constexpr (MODE == M_GRAD) {
+              const P2 cc = pmul(om, coef);
 #pragma unroll
-              for (int c = 0; c < CW; ++c) {
-                const T w = rowv[F2 + c];
-                sc[j][c] = fma(w, k, sc[j][c]);
-                if constexpr (MODE == M_GRAD) om = fma(go[j][c], w, om);
-                if constexpr (MODE == M_JAC) {
-                  const T cv = w * coef;
-                  const P cc(cv, cv);
-#pragma unroll
-                  for (int p = 0; p < FP; ++p) g[j][c][p] = pfma(cc, d[p], g[j][c][p]);
-                }
-              }
-              if constexpr (MODE == M_GRAD) {
-                const T cv = om * coef;
-                const P cc(cv, cv);
-#pragma unroll
-                for (int p = 0; p < FP; ++p) g[j][0][p] = pfma(cc, d[p], g[j][0][p]);
-              }
+              for (int f = 0; f < F; ++f) g[f] = pfma(cc, d[f], g[f]);
             }
           }
         }
@@ -242,18 +240,12 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
       }
 
       // ---- combine the NW partial sums of every query (fixed order) ----------------------------------
+      {
+        float2* rq = reinterpret_cast<float2*>(red + (size_t)warp * NRED * QT) + lane;
 #pragma unroll
-      for (int j = 0; j < Q; ++j) {
-        T* rq = red + (size_t)warp * NRED * QT + lane + 32 * j;
+        for (int c = 0; c < CW; ++c) rq[(size_t)c * (QT / 2)] = sc[c].v;
 #pragma unroll
-        for (int c = 0; c < CW; ++c) rq[(size_t)c * QT] = sc[j][c];
-#pragma unroll
-        for (int gi2 = 0; gi2 < NG; ++gi2)
-#pragma unroll
-          for (int p = 0; p < FP; ++p) {
-            rq[(size_t)(CW + gi2 * F2 + 2 * p) * QT] = g[j][gi2][p].lo();
-            rq[(size_t)(CW + gi2 * F2 + 2 * p + 1) * QT] = g[j][gi2][p].hi();
-          }
+        for (int f = 0; f < NG * F; ++f) rq[(size_t)(CW + f) * (QT / 2)] = g[f].v;
       }
       __syncthreads();
       for (int idx = tid; idx < NRED * QT; idx += NT) {
@@ -263,7 +255,7 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
         for (int w = 0; w < NW; ++w) s += red[((size_t)w * NRED + kk) * QT + qi];
         if (kk < CW) {
           const long long b = b_base + toff + qi;
-          if (kk < a.n_class && b < a.batch) a.score[(size_t)b * a.score_ld + kk] = s * a.rc.score_scale;
+          if (kk < a.n_class && b < a.batch && a.write_score) a.score[(size_t)b * a.score_ld + kk] = s * a.rc.score_scale;
         } else {
           gs[(size_t)(kk - CW) * ST + toff + qi] = s * a.rc.grad_scale;
         }
@@ -272,33 +264,25 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
     }
 
     // ---- phase C: J_FK^T g_x, one query per thread ---------------------------------------------------
-    if constexpr (MODE != M_SCORE) {
+    if constexpr (MODE == M_GRAD) {
       if (tid < nq) {
         const long long b = b_base + tid;
         const T* qp = a.q + (size_t)b * a.n_in;
+        T scale = (T)1;
+        if (CW == 1 && a.grad_out != nullptr) scale = a.grad_out[b];
+        T* out = a.grad + (size_t)b * a.grad_ld + (a.jac_class > 0 ? (size_t)a.jac_class * a.n_in : 0);
         if (a.fk.type == DC_FK_NONE) {
-          for (int gi2 = 0; gi2 < NG; ++gi2) {
-            if (MODE == M_JAC && gi2 >= a.n_class) break;
-            T scale = (T)1;
-            if (MODE == M_GRAD && CW == 1 && a.grad_out != nullptr) scale = a.grad_out[b];
-            T* out = a.grad + (size_t)b * a.grad_ld + (MODE == M_JAC ? (size_t)gi2 * a.n_in : 0);
-            for (int f = 0; f < a.n_feat; ++f) out[f] = scale * gs[((size_t)gi2 * F2 + f) * ST + tid];
-          }
+#pragma unroll
+          for (int f = 0; f < F; ++f) out[f] = scale * gs[(size_t)f * ST + tid];
         } else {
-          T qv[DC_MAX_DOF];
+          T qv[DC_MAX_DOF], gq[DC_MAX_DOF];
 #pragma unroll
-          for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < a.n_in) ? qp[i] : (T)0;
-          for (int gi2 = 0; gi2 < NG; ++gi2) {
-            if (MODE == M_JAC && gi2 >= a.n_class) break;
-            T gq[DC_MAX_DOF];
-#pragma unroll
-            for (int i = 0; i < DC_MAX_DOF; ++i) gq[i] = (T)0;
-            fk_vjp<T>(a.fk, qv, xs + tid, ST, gs + (size_t)gi2 * F2 * ST + tid, ST, gq);
-            T scale = (T)1;
-            if (MODE == M_GRAD && CW == 1 && a.grad_out != nullptr) scale = a.grad_out[b];
-            T* out = a.grad + (size_t)b * a.grad_ld + (MODE == M_JAC ? (size_t)gi2 * a.n_in : 0);
-            for (int i = 0; i < a.n_in; ++i) out[i] = scale * gq[i];
+          for (int i = 0; i < DC_MAX_DOF; ++i) {
+            qv[i] = (i < a.n_in) ? qp[i] : (T)0;
+            gq[i] = (T)0;
           }
+          fk_vjp<T>(a.fk, qv, xs + tid, ST, gs + tid, ST, gq);
+          for (int i = 0; i < a.n_in; ++i) out[i] = scale * gq[i];
         }
       }
       __syncthreads();
@@ -306,10 +290,11 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
   }
 }
 
-// Host-side launcher for one instantiation.  Returns false when the configuration does not fit shared memory.
-template <int FP, int KIND, int CW, int MODE, int Q, int NW, int STAGES>
+// Host-side launcher for one instantiation.  Returns DC_ERR_UNSUPPORTED when the configuration does not fit shared
+// memory (the caller falls back to the lane-split kernel).
+template <int F, int KIND, int CW, int MODE, int NW, int STAGES>
 int launch_score_tq(ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
-  using Cfg = TqCfg<FP, CW, MODE, Q, NW, STAGES>;
+  using Cfg = TqCfg<F, CW, MODE, NW, STAGES>;
   constexpr size_t kMaxSmem = 227 * 1024;
   int st_q = Cfg::NT, ch = 32;
   // shrink the ring chunk, then the super-tile, until the CTA fits
@@ -320,7 +305,7 @@ int launch_score_tq(ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
   a.chunk_rows = ch;
   a.n_tiles = (int)ceil_div64(a.batch, Cfg::QT);
   const size_t smem = Cfg::smem_bytes(st_q, ch);
-  auto kern = score_tq_kernel<FP, KIND, CW, MODE, Q, NW, STAGES>;
+  auto kern = score_tq_kernel<F, KIND, CW, MODE, NW, STAGES>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     DC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));

@@ -9,28 +9,36 @@
 
 namespace dc {
 
-// Q (queries per lane): 2 where the register file allows it, 1 for the wide multi-class modes.
-template <int FP>
-static int launch_fp(ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
-  constexpr int CW = DC_TQ_CW;
-  constexpr int MODE = DC_TQ_MODE;
-  constexpr int NG = (MODE == M_JAC) ? CW : (MODE == M_GRAD ? 1 : 0);
-  constexpr int Q = ((2 + NG) * FP * 2 * 2 + 2 * CW * 2 > 96) ? 1 : 2;
-  return launch_score_tq<FP, DC_TQ_KIND, CW, MODE, Q, 16, 3>(a, num_sms, stream);
+// Feature counts of the reference's feature maps (diffco/model.py): planar chains 2..8 links, SE(2)/SE(3) bodies,
+// Baxter (12 / 24), Panda (21; 15 in robot_fkine.py), raw configurations.  Up to 14 features the per-lane state
+// (x, d, g: 3F packed registers) fits 128 registers and the CTA runs 16 warps; above that 8 warps with 255 registers.
+template <int F>
+static int launch_f(ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
+  constexpr int NW = (F <= 14) ? 16 : 8;
+  return launch_score_tq<F, DC_TQ_KIND, DC_TQ_CW, DC_TQ_MODE, NW, 3>(a, num_sms, stream);
 }
 
-int DC_TQ_NAME(int fp, ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
-  switch (fp) {
-    case 1: return launch_fp<1>(a, num_sms, stream);
-    case 2: return launch_fp<2>(a, num_sms, stream);
-    case 3: return launch_fp<3>(a, num_sms, stream);
-    case 4: return launch_fp<4>(a, num_sms, stream);
-    case 6: return launch_fp<6>(a, num_sms, stream);
-    case 7: return launch_fp<7>(a, num_sms, stream);
-    case 8: return launch_fp<8>(a, num_sms, stream);
-    case 11: return launch_fp<11>(a, num_sms, stream);
-    case 12: return launch_fp<12>(a, num_sms, stream);
-    default: return DC_ERR_UNSUPPORTED;
+int DC_TQ_NAME(int n_feat, ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
+  switch (n_feat) {
+#define DC_TQ_CASE(F) \
+  case F:             \
+    return launch_f<F>(a, num_sms, stream);
+    DC_TQ_CASE(2)
+    DC_TQ_CASE(3)
+    DC_TQ_CASE(4)
+    DC_TQ_CASE(6)
+    DC_TQ_CASE(7)
+    DC_TQ_CASE(8)
+    DC_TQ_CASE(10)
+    DC_TQ_CASE(12)
+    DC_TQ_CASE(14)
+    DC_TQ_CASE(15)
+    DC_TQ_CASE(16)
+    DC_TQ_CASE(21)
+    DC_TQ_CASE(24)
+#undef DC_TQ_CASE
+    default:
+      return DC_ERR_UNSUPPORTED;
   }
 }
 

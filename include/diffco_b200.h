@@ -106,7 +106,8 @@ typedef struct dc_kernel_desc {
   double param;
 } dc_kernel_desc;
 
-/* Support set packed for the fused kernels: row n = [-s_n[0..F) zero-padded to f_pad | w[n,0..C) zero-padded]. */
+/* Support set packed for the fused kernels: row n = [-s_n[0..F) zero-padded to f_pad | w[n,0..C) zero-padded to 1 or a
+ * multiple of 4 classes], rows padded to a multiple of 4 elements (16-byte aligned for float). */
 typedef struct dc_supports {
   const void* table;   /* device, [n][row_stride] of dtype, 16-byte aligned rows */
   int64_t n;           /* N support vectors */
