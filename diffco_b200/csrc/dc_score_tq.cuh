@@ -6,13 +6,13 @@
 // fkine -> torch.cdist -> pow/reciprocal -> matmul and the autograd backward of all of them
 // (diffco/kernel_perceptrons.py:309-319,362-370; diffco/kernel.py:17-79; diffco/model.py:40-48,225-241).
 //
-// Work decomposition (B200: 148 SMs, one persistent NW-warp CTA per SM):
-//   * the batch is cut into tiles of QT = 64 queries; CTA i owns a contiguous, balanced range of tiles;
-//   * tiles are staged in super-tiles of up to NT = 32*NW queries: phase A runs FK one-query-per-thread into
-//     shared memory (xs[F][ST], conflict-free columns), phase C runs the J^T product the same way;
-//   * phase B, per tile: lane l of EVERY warp holds queries (2l, 2l+1) of the tile as the two halves of packed
-//     registers, and the NW warps split the support set into NW contiguous slices, so all warps stay busy on any
-//     batch that fills the SMs and the tail quantises at 64 queries;
+// Work decomposition (B200: 148 SMs, one persistent 16-warp CTA per SM):
+//   * the batch is cut into tiles of QT = 64 queries; CTA i owns a contiguous, balanced range of tiles and deals them
+//     round-robin to its 16/NWG warp groups; a group synchronises only with itself (named barriers);
+//   * per tile, phase A runs FK one-query-per-thread into shared memory (xs[F][64], conflict-free columns) and phase C
+//     runs the J^T product the same way;
+//   * phase B: lane l of every warp of the group holds queries (2l, 2l+1) of the tile as the two halves of packed
+//     registers, and the group's NWG warps split the support set into NWG contiguous slices;
 //   * each warp streams its own slice of the packed support table HBM/L2 -> shared memory with 1-D bulk TMA
 //     (cp.async.bulk + mbarrier complete_tx) through a private STAGES-deep ring, running STAGES chunks ahead and
 //     prefetching across tile boundaries; rows are read back as warp-uniform LDS.128 broadcasts;
@@ -55,45 +55,59 @@ struct ScoreArgs {
   int chunk_rows;
 };
 
-template <int F, int CW, int MODE, int NW, int STAGES>
+// NWG = warps per group (4 or 16).  A CTA always has 16 warps = 16/NWG groups; a group owns one 64-query tile at a time
+// and its NWG warps split the support set.  NWG = 4 (four concurrent tiles per SM, group-local named barriers, 4-way
+// reduction) is the throughput configuration; NWG = 16 (one tile per SM at a time) keeps every warp busy when the
+// batch has fewer than ~4 tiles per SM.
+template <int F, int CW, int MODE, int NWG, int STAGES>
 struct TqCfg {
+  static constexpr int NW = 16;
+  static constexpr int NGRP = NW / NWG;
+  static constexpr int GT = NWG * 32;  // threads per group
   static constexpr int FPAD = round_up(F, 2);
   static constexpr int ROW = round_up(FPAD + CW, 4);
   static constexpr int QT = 64;
-  static constexpr int NT = 32 * NW;
   static constexpr int NG = (MODE == M_GRAD) ? 1 : 0;
   static constexpr int NRED = CW + NG * F;
   static constexpr int BAR_BYTES = round_up(NW * STAGES * 8, 128);
-  __host__ __device__ static constexpr size_t smem_bytes(int st_q, int chunk_rows) {
-    return (size_t)BAR_BYTES + sizeof(float) * ((size_t)NW * STAGES * chunk_rows * ROW + (size_t)NW * NRED * QT +
-                                                (size_t)F * st_q + (size_t)NG * F * st_q);
+  __host__ __device__ static constexpr size_t smem_bytes(int chunk_rows) {
+    return (size_t)BAR_BYTES +
+           sizeof(float) * ((size_t)NW * STAGES * chunk_rows * ROW + (size_t)NW * NRED * QT + (size_t)NGRP * (1 + NG) * F * QT);
   }
 };
 
-template <int F, int KIND, int CW, int MODE, int NW, int STAGES>
-__global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_constant__ ScoreArgs<float> a) {
+__device__ __forceinline__ void group_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int F, int KIND, int CW, int MODE, int NWG, int STAGES>
+__global__ void __launch_bounds__(512, 1) score_tq_kernel(const __grid_constant__ ScoreArgs<float> a) {
   using T = float;
-  using Cfg = TqCfg<F, CW, MODE, NW, STAGES>;
-  constexpr int FPAD = Cfg::FPAD, ROW = Cfg::ROW, QT = Cfg::QT, NT = Cfg::NT, NG = Cfg::NG, NRED = Cfg::NRED;
+  using Cfg = TqCfg<F, CW, MODE, NWG, STAGES>;
+  constexpr int NW = Cfg::NW, NGRP = Cfg::NGRP, GT = Cfg::GT;
+  constexpr int FPAD = Cfg::FPAD, ROW = Cfg::ROW, QT = Cfg::QT, NG = Cfg::NG, NRED = Cfg::NRED;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ST = a.st_q, CH = a.chunk_rows;
+  const int grp = warp / NWG, wig = warp - grp * NWG, gtid = tid - grp * GT;  // group, warp in group, thread in group
+  const int CH = a.chunk_rows;
+  const int bar_id = 1 + grp;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * STAGES;
   T* ring_all = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES);
   T* ring = ring_all + (size_t)warp * STAGES * CH * ROW;
-  T* red = ring_all + (size_t)NW * STAGES * CH * ROW;
-  T* xs = red + (size_t)NW * NRED * QT;
-  T* gs = xs + (size_t)F * ST;
+  T* red = ring_all + (size_t)NW * STAGES * CH * ROW + (size_t)grp * NWG * NRED * QT;  // [wig][kk][QT]
+  T* xs = ring_all + (size_t)NW * STAGES * CH * ROW + (size_t)NW * NRED * QT + (size_t)grp * (1 + NG) * F * QT;  // [F][QT]
+  T* gs = xs + (size_t)F * QT;                                                                                    // [F][QT]
 
-  // ---- this CTA's tiles and this warp's slice of the support set ---------------------------------
+  // ---- this CTA's tiles (contiguous, balanced), dealt round-robin to its groups; this warp's slice of the supports
   const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
   const long long t1 = (long long)(blockIdx.x + 1) * a.n_tiles / gridDim.x;
-  const int n0 = (int)((long long)warp * a.n_sv / NW);
-  const int n1 = (int)((long long)(warp + 1) * a.n_sv / NW);
+  const long long my_tiles = (t1 - t0 > grp) ? (t1 - t0 - grp + NGRP - 1) / NGRP : 0;
+  const int n0 = (int)((long long)wig * a.n_sv / NWG);
+  const int n1 = (int)((long long)(wig + 1) * a.n_sv / NWG);
   const int n_chunks = (n1 - n0 + CH - 1) / CH;
-  const long long total_chunks = (long long)n_chunks * (t1 - t0);
+  const long long total_chunks = (long long)n_chunks * my_tiles;
 
   if (lane == 0) {
 #pragma unroll
@@ -102,178 +116,181 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
   }
   __syncwarp();
 
-  auto issue = [&](long long gi) {  // lane 0 only: fetch chunk (gi % n_chunks) of the slice into stage gi % STAGES
-    const int ci = (int)(gi % n_chunks);
-    const int stage = (int)(gi % STAGES);
-    const int r0 = n0 + ci * CH;
+  // producer state (lane 0): next chunk of the slice to fetch and the stage it goes to; chunks are fetched in slice
+  // order over and over, once per tile, so the ring runs ahead across tile boundaries
+  long long issued = 0;
+  int ci_issue = 0, st_issue = 0;
+  auto issue = [&]() {
+    const int r0 = n0 + ci_issue * CH;
     const int rows = min(CH, n1 - r0);
     const uint32_t bytes = (uint32_t)rows * ROW * sizeof(T);
-    mbar_expect_tx(&bars[stage], bytes);
-    tma_bulk_g2s(ring + (size_t)stage * CH * ROW, a.table + (size_t)r0 * ROW, bytes, &bars[stage]);
+    mbar_expect_tx(&bars[st_issue], bytes);
+    tma_bulk_g2s(ring + (size_t)st_issue * CH * ROW, a.table + (size_t)r0 * ROW, bytes, &bars[st_issue]);
+    ++issued;
+    if (++ci_issue == n_chunks) ci_issue = 0;
+    if (++st_issue == STAGES) st_issue = 0;
   };
   if (lane == 0) {
-    for (long long gi = 0; gi < STAGES && gi < total_chunks; ++gi) issue(gi);
+    for (int s = 0; s < STAGES && issued < total_chunks; ++s) issue();
   }
-  long long gi = 0;  // chunks consumed so far by this warp
+  int st_use = 0;
+  uint32_t parity = 0;
 
-  const int tiles_per_st = ST / QT;
-  for (long long st0 = t0; st0 < t1; st0 += tiles_per_st) {
-    const int nt = (int)min((long long)tiles_per_st, t1 - st0);
-    const long long b_base = st0 * QT;
-    const int nq = (int)min((long long)nt * QT, a.batch - b_base);
+  for (long long tile = t0 + grp; tile < t1; tile += NGRP) {
+    const long long b_base = tile * QT;
+    const int nq = (int)min((long long)QT, a.batch - b_base);
 
     // ---- phase A: FK, one query per thread, features into xs[f][t] ---------------------------------
-    if (tid < nt * QT) {
-      if (tid < nq) {
-        const T* qp = a.q + (size_t)(b_base + tid) * a.n_in;
+    if (gtid < QT) {
+      if (gtid < nq) {
+        const T* qp = a.q + (size_t)(b_base + gtid) * a.n_in;
         if (a.fk.type == DC_FK_NONE) {
 #pragma unroll
-          for (int f = 0; f < F; ++f) xs[(size_t)f * ST + tid] = qp[f];
+          for (int f = 0; f < F; ++f) xs[f * QT + gtid] = qp[f];
         } else {
           T qv[DC_MAX_DOF];
 #pragma unroll
           for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < a.n_in) ? qp[i] : (T)0;
-          fk_forward<T>(a.fk, qv, xs + tid, ST);
+          fk_forward<T>(a.fk, qv, xs + gtid, QT);
         }
       } else {
 #pragma unroll
-        for (int f = 0; f < F; ++f) xs[(size_t)f * ST + tid] = (T)0;
+        for (int f = 0; f < F; ++f) xs[f * QT + gtid] = (T)0;
       }
     }
-    __syncthreads();
+    group_barrier(bar_id, GT);
 
-    // ---- phase B: tiles ---------------------------------------------------------------------------
-    for (int tl = 0; tl < nt; ++tl) {
-      const int toff = tl * QT;
-      P2 x[F];
-      P2 sc[CW];
-      P2 g[NG > 0 ? F : 1];
-      P2 go[CW];
+    // ---- phase B: this warp's slice of the supports against the tile's 64 queries (2 per lane) ------
+    P2 x[F];
+    P2 sc[CW];
+    P2 g[NG > 0 ? F : 1];
+    P2 go[CW];
 #pragma unroll
-      for (int f = 0; f < F; ++f) x[f] = P2(*reinterpret_cast<const float2*>(xs + (size_t)f * ST + toff + 2 * lane));
+    for (int f = 0; f < F; ++f) x[f] = P2(*reinterpret_cast<const float2*>(xs + f * QT + 2 * lane));
 #pragma unroll
-      for (int c = 0; c < CW; ++c) {
-        sc[c] = P2(0.f, 0.f);
-        go[c] = P2(1.f, 1.f);
+    for (int c = 0; c < CW; ++c) {
+      sc[c] = P2(0.f, 0.f);
+      go[c] = P2(1.f, 1.f);
+    }
+#pragma unroll
+    for (int f = 0; f < (NG > 0 ? F : 1); ++f) g[f] = P2(0.f, 0.f);
+    if constexpr (MODE == M_GRAD && CW > 1) {
+      if (a.jac_class >= 0) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) go[c] = (c == a.jac_class) ? P2(1.f, 1.f) : P2(0.f, 0.f);
+      } else {
+        const long long b = b_base + 2 * lane;
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+          T v0 = (c < a.n_class) ? (T)1 : (T)0, v1 = v0;
+          if (a.grad_out != nullptr && c < a.n_class) {
+            v0 = (b < a.batch) ? a.grad_out[(size_t)b * a.n_class + c] : (T)0;
+            v1 = (b + 1 < a.batch) ? a.grad_out[(size_t)(b + 1) * a.n_class + c] : (T)0;
+          }
+          go[c] = P2(v0, v1);
+        }
       }
+    }
+
+    for (int ci = 0; ci < n_chunks; ++ci) {
+      mbar_wait(&bars[st_use], parity);
+      const T* buf = ring + (size_t)st_use * CH * ROW;
+      const int rows = min(CH, n1 - (n0 + ci * CH));
+#pragma unroll 2
+      for (int r = 0; r < rows; ++r) {
+        T rowv[ROW];
+        const float4* rp = reinterpret_cast<const float4*>(buf + (size_t)r * ROW);
 #pragma unroll
-      for (int f = 0; f < (NG > 0 ? F : 1); ++f) g[f] = P2(0.f, 0.f);
-      if constexpr (MODE == M_GRAD && CW > 1) {
-        if (a.jac_class >= 0) {
+        for (int i = 0; i < ROW / 4; ++i) {
+          const float4 v = rp[i];
+          rowv[4 * i] = v.x;
+          rowv[4 * i + 1] = v.y;
+          rowv[4 * i + 2] = v.z;
+          rowv[4 * i + 3] = v.w;
+        }
+        P2 d[F];
 #pragma unroll
-          for (int c = 0; c < CW; ++c) go[c] = (c == a.jac_class) ? P2(1.f, 1.f) : P2(0.f, 0.f);
+        for (int f = 0; f < F; ++f) d[f] = padd_b(x[f], rowv[f]);  // the table holds -s
+        P2 acc0 = pmul(d[0], d[0]);
+        P2 acc1(0.f, 0.f);
+#pragma unroll
+        for (int f = 1; f < F; ++f) {
+          if (f & 1)
+            acc1 = (f == 1) ? pmul(d[f], d[f]) : pfma(d[f], d[f], acc1);
+          else
+            acc0 = pfma(d[f], d[f], acc0);
+        }
+        if constexpr (F > 1) acc0 = padd(acc0, acc1);
+        P2 k, coef;
+        radial_eval2<KIND>(a.rc, acc0, k, coef);
+        if constexpr (CW == 1) {
+          const T w = rowv[FPAD];
+          sc[0] = pfma_b(w, k, sc[0]);
+          if constexpr (MODE == M_GRAD) {
+            const P2 cc = pmul_b(coef, w);
+#pragma unroll
+            for (int f = 0; f < F; ++f) g[f] = pfma(cc, d[f], g[f]);
+          }
         } else {
-          const long long b = b_base + toff + 2 * lane;
+          P2 om(0.f, 0.f);
 #pragma unroll
           for (int c = 0; c < CW; ++c) {
-            T v0 = (c < a.n_class) ? (T)1 : (T)0, v1 = v0;
-            if (a.grad_out != nullptr && c < a.n_class) {
-              v0 = (b < a.batch) ? a.grad_out[(size_t)b * a.n_class + c] : (T)0;
-              v1 = (b + 1 < a.batch) ? a.grad_out[(size_t)(b + 1) * a.n_class + c] : (T)0;
-            }
-            go[c] = P2(v0, v1);
+            const T w = rowv[FPAD + c];
+            sc[c] = pfma_b(w, k, sc[c]);
+            if constexpr (MODE == M_GRAD) om = pfma_b(w, go[c], om);
+          }
+          if constexpr (MODE == M_GRAD) {
+            const P2 cc = pmul(om, coef);
+#pragma unroll
+            for (int f = 0; f < F; ++f) g[f] = pfma(cc, d[f], g[f]);
           }
         }
       }
+      __syncwarp();
+      if (lane == 0 && issued < total_chunks) {
+        fence_proxy_async();
+        issue();  // refills exactly the stage that was just drained
+      }
+      if (++st_use == STAGES) {
+        st_use = 0;
+        parity ^= 1u;
+      }
+    }
 
-      for (int ci = 0; ci < n_chunks; ++ci, ++gi) {
-        const int stage = (int)(gi % STAGES);
-        const uint32_t parity = (uint32_t)((gi / STAGES) & 1);
-        mbar_wait(&bars[stage], parity);
-        const T* buf = ring + (size_t)stage * CH * ROW;
-        const int rows = min(CH, n1 - (n0 + ci * CH));
-#pragma unroll 2
-        for (int r = 0; r < rows; ++r) {
-          T rowv[ROW];
-          const float4* rp = reinterpret_cast<const float4*>(buf + (size_t)r * ROW);
+    // ---- combine the NWG partial sums of every query (fixed order) -----------------------------------
+    {
+      float2* rq = reinterpret_cast<float2*>(red + (size_t)wig * NRED * QT) + lane;
 #pragma unroll
-          for (int i = 0; i < ROW / 4; ++i) {
-            const float4 v = rp[i];
-            rowv[4 * i] = v.x;
-            rowv[4 * i + 1] = v.y;
-            rowv[4 * i + 2] = v.z;
-            rowv[4 * i + 3] = v.w;
-          }
-          P2 d[F];
+      for (int c = 0; c < CW; ++c) rq[c * (QT / 2)] = sc[c].v;
 #pragma unroll
-          for (int f = 0; f < F; ++f) d[f] = padd_b(x[f], rowv[f]);  // the table holds -s
-          P2 acc0 = pmul(d[0], d[0]);
-          P2 acc1(0.f, 0.f);
+      for (int f = 0; f < NG * F; ++f) rq[(CW + f) * (QT / 2)] = g[f].v;
+    }
+    group_barrier(bar_id, GT);
+    for (int idx = gtid; idx < NRED * QT; idx += GT) {
+      const int kk = idx / QT, qi = idx - kk * QT;
+      T s = (T)0;
 #pragma unroll
-          for (int f = 1; f < F; ++f) {
-            if (f & 1)
-              acc1 = (f == 1) ? pmul(d[f], d[f]) : pfma(d[f], d[f], acc1);
-            else
-              acc0 = pfma(d[f], d[f], acc0);
-          }
-          if constexpr (F > 1) acc0 = padd(acc0, acc1);
-          P2 k, coef;
-          radial_eval2<KIND>(a.rc, acc0, k, coef);
-          if constexpr (CW == 1) {
-            const T w = rowv[FPAD];
-            sc[0] = pfma_b(w, k, sc[0]);
-            if constexpr (MODE == M_GRAD) {
-              const P2 cc = pmul_b(coef, w);
-#pragma unroll
-              for (int f = 0; f < F; ++f) g[f] = pfma(cc, d[f], g[f]);
-            }
-          } else {
-            P2 om(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < CW; ++c) {
-              const T w = rowv[FPAD + c];
-              sc[c] = pfma_b(w, k, sc[c]);
-              if constexpr (MODE == M_GRAD) om = pfma_b(w, go[c], om);
-            }
-            if constexpr (MODE == M_GRAD) {
-              const P2 cc = pmul(om, coef);
-#pragma unroll
-              for (int f = 0; f < F; ++f) g[f] = pfma(cc, d[f], g[f]);
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0 && gi + STAGES < total_chunks) {
-          fence_proxy_async();
-          issue(gi + STAGES);
-        }
+      for (int w = 0; w < NWG; ++w) s += red[(w * NRED + kk) * QT + qi];
+      if (kk < CW) {
+        const long long b = b_base + qi;
+        if (kk < a.n_class && b < a.batch && a.write_score) a.score[(size_t)b * a.score_ld + kk] = s * a.rc.score_scale;
+      } else {
+        gs[(kk - CW) * QT + qi] = s * a.rc.grad_scale;
       }
-
-      // ---- combine the NW partial sums of every query (fixed order) ----------------------------------
-      {
-        float2* rq = reinterpret_cast<float2*>(red + (size_t)warp * NRED * QT) + lane;
-#pragma unroll
-        for (int c = 0; c < CW; ++c) rq[(size_t)c * (QT / 2)] = sc[c].v;
-#pragma unroll
-        for (int f = 0; f < NG * F; ++f) rq[(size_t)(CW + f) * (QT / 2)] = g[f].v;
-      }
-      __syncthreads();
-      for (int idx = tid; idx < NRED * QT; idx += NT) {
-        const int kk = idx / QT, qi = idx - kk * QT;
-        T s = (T)0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) s += red[((size_t)w * NRED + kk) * QT + qi];
-        if (kk < CW) {
-          const long long b = b_base + toff + qi;
-          if (kk < a.n_class && b < a.batch && a.write_score) a.score[(size_t)b * a.score_ld + kk] = s * a.rc.score_scale;
-        } else {
-          gs[(size_t)(kk - CW) * ST + toff + qi] = s * a.rc.grad_scale;
-        }
-      }
-      __syncthreads();
     }
 
     // ---- phase C: J_FK^T g_x, one query per thread ---------------------------------------------------
     if constexpr (MODE == M_GRAD) {
-      if (tid < nq) {
-        const long long b = b_base + tid;
+      group_barrier(bar_id, GT);
+      if (gtid < nq) {
+        const long long b = b_base + gtid;
         const T* qp = a.q + (size_t)b * a.n_in;
         T scale = (T)1;
         if (CW == 1 && a.grad_out != nullptr) scale = a.grad_out[b];
         T* out = a.grad + (size_t)b * a.grad_ld + (a.jac_class > 0 ? (size_t)a.jac_class * a.n_in : 0);
         if (a.fk.type == DC_FK_NONE) {
 #pragma unroll
-          for (int f = 0; f < F; ++f) out[f] = scale * gs[(size_t)f * ST + tid];
+          for (int f = 0; f < F; ++f) out[f] = scale * gs[f * QT + gtid];
         } else {
           T qv[DC_MAX_DOF], gq[DC_MAX_DOF];
 #pragma unroll
@@ -281,38 +298,36 @@ __global__ void __launch_bounds__(NW * 32, 1) score_tq_kernel(const __grid_const
             qv[i] = (i < a.n_in) ? qp[i] : (T)0;
             gq[i] = (T)0;
           }
-          fk_vjp<T>(a.fk, qv, xs + tid, ST, gs + tid, ST, gq);
+          fk_vjp<T>(a.fk, qv, xs + gtid, QT, gs + gtid, QT, gq);
           for (int i = 0; i < a.n_in; ++i) out[i] = scale * gq[i];
         }
       }
-      __syncthreads();
     }
+    group_barrier(bar_id, GT);  // xs / gs / red are rewritten by the next tile
   }
 }
 
 // Host-side launcher for one instantiation.  Returns DC_ERR_UNSUPPORTED when the configuration does not fit shared
 // memory (the caller falls back to the lane-split kernel).
-template <int F, int KIND, int CW, int MODE, int NW, int STAGES>
+template <int F, int KIND, int CW, int MODE, int NWG, int STAGES>
 int launch_score_tq(ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
-  using Cfg = TqCfg<F, CW, MODE, NW, STAGES>;
+  using Cfg = TqCfg<F, CW, MODE, NWG, STAGES>;
   constexpr size_t kMaxSmem = 227 * 1024;
-  int st_q = Cfg::NT, ch = 32;
-  // shrink the ring chunk, then the super-tile, until the CTA fits
-  while (Cfg::smem_bytes(st_q, ch) > kMaxSmem && ch > 4) ch >>= 1;
-  while (Cfg::smem_bytes(st_q, ch) > kMaxSmem && st_q > Cfg::QT) st_q >>= 1;
-  if (Cfg::smem_bytes(st_q, ch) > kMaxSmem) return DC_ERR_UNSUPPORTED;
-  a.st_q = st_q;
+  int ch = 32;
+  while (Cfg::smem_bytes(ch) > kMaxSmem && ch > 4) ch >>= 1;  // shrink the ring chunk until the CTA fits
+  if (Cfg::smem_bytes(ch) > kMaxSmem) return DC_ERR_UNSUPPORTED;
+  a.st_q = Cfg::QT;
   a.chunk_rows = ch;
   a.n_tiles = (int)ceil_div64(a.batch, Cfg::QT);
-  const size_t smem = Cfg::smem_bytes(st_q, ch);
-  auto kern = score_tq_kernel<F, KIND, CW, MODE, NW, STAGES>;
+  const size_t smem = Cfg::smem_bytes(ch);
+  auto kern = score_tq_kernel<F, KIND, CW, MODE, NWG, STAGES>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     DC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     attr_set = true;
   }
-  const int grid = (int)min((long long)num_sms, (long long)a.n_tiles);
-  kern<<<grid, Cfg::NT, smem, stream>>>(a);
+  const int grid = (int)min((long long)num_sms, (long long)ceil_div64(a.n_tiles, Cfg::NGRP));
+  kern<<<grid, 512, smem, stream>>>(a);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -10,12 +10,14 @@
 namespace dc {
 
 // Feature counts of the reference's feature maps (diffco/model.py): planar chains 2..8 links, SE(2)/SE(3) bodies,
-// Baxter (12 / 24), Panda (21; 15 in robot_fkine.py), raw configurations.  Up to 14 features the per-lane state
-// (x, d, g: 3F packed registers) fits 128 registers and the CTA runs 16 warps; above that 8 warps with 255 registers.
+// Baxter (12 / 24), Panda (21; 15 in robot_fkine.py), raw configurations.  The per-lane state (x, d, g: 3F packed
+// registers) must fit the 128 registers a 512-thread CTA leaves per thread; wider maps take the lane-split kernel.
 template <int F>
 static int launch_f(ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
-  constexpr int NW = (F <= 14) ? 16 : 8;
-  return launch_score_tq<F, DC_TQ_KIND, DC_TQ_CW, DC_TQ_MODE, NW, 3>(a, num_sms, stream);
+  // four concurrent tiles per SM when there are enough tiles to go around, one 16-warp tile otherwise
+  const long long tiles = (a.batch + 63) / 64;
+  if (tiles >= 3LL * num_sms) return launch_score_tq<F, DC_TQ_KIND, DC_TQ_CW, DC_TQ_MODE, 4, 3>(a, num_sms, stream);
+  return launch_score_tq<F, DC_TQ_KIND, DC_TQ_CW, DC_TQ_MODE, 16, 3>(a, num_sms, stream);
 }
 
 int DC_TQ_NAME(int n_feat, ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
@@ -34,8 +36,6 @@ int DC_TQ_NAME(int n_feat, ScoreArgs<float>& a, int num_sms, cudaStream_t stream
     DC_TQ_CASE(14)
     DC_TQ_CASE(15)
     DC_TQ_CASE(16)
-    DC_TQ_CASE(21)
-    DC_TQ_CASE(24)
 #undef DC_TQ_CASE
     default:
       return DC_ERR_UNSUPPORTED;

@@ -513,12 +513,17 @@ def _full_size_checks(rname, kname, N, C, B, dev, seed, n_sample=384):
     assert rel(g[idx.to(dev)], g_ref) <= 1e-5
 
     # (2) position independence: the same configurations in a different batch (reversed order, and a ragged slice
-    #     starting mid-tile) give bit-identical rows — the reduction order over support vectors is fixed
+    #     starting mid-tile) give bit-identical rows — the reduction order over support vectors is fixed for a given
+    #     launch configuration
     s_r, g_r = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd.flip(0).contiguous(), _lib.DC_GRAD_SUM, god.flip(0).contiguous())
     assert torch.equal(s_r.flip(0), s) and torch.equal(g_r.flip(0), g)
-    lo, hi = 12345, 12345 + 7001
+    lo, hi = 12345, 12345 + 40001
     s_p, g_p = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd[lo:hi].contiguous(), _lib.DC_GRAD_SUM, god[lo:hi].contiguous())
     assert torch.equal(s_p, s[lo:hi]) and torch.equal(g_p, g[lo:hi])
+    # a small slice takes a different launch configuration (16 warps per tile instead of 4): same values to rounding
+    s_p, g_p = Fn.score_grad(robot.fk_desc, kfun.desc, sv, qd[lo:lo + 5001].contiguous(), _lib.DC_GRAD_SUM,
+                             god[lo:lo + 5001].contiguous())
+    assert rel(s_p, s[lo:lo + 5001]) <= 5e-6 and rel(g_p, g[lo:lo + 5001]) <= 5e-6
 
     # (3) linearity in the weights: score(W1 + W2) == score(W1) + score(W2) (to rounding)
     W2 = torch.randn(N, C, generator=gen, dtype=torch.float64)
