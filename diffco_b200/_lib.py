@@ -90,6 +90,10 @@ PROTOTYPES = {
     "dc_pack_supports": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_score_grad": (C.c_int, [C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "dc_host_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int32]),
+    "dc_host_pipeline_destroy": (None, [C.c_void_p]),
+    "dc_score_grad_host": (C.c_int, [C.c_void_p, C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p,
+                                     C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "dc_kernel_matrix": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_fk_forward": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),

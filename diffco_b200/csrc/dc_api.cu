@@ -209,6 +209,22 @@ static int score_grad_generic(const dc_fk_desc* fk, const dc_kernel_desc* kernel
 // Batches below this go to the lane-split kernel (too few 64-query tiles to occupy the SMs).
 static constexpr int64_t kTqMinBatch = 2048;
 
+static bool tq_feature_count(int f) {  // keep in sync with the switch in dc_score_tq_inst.cu
+  switch (f) {
+    case 2: case 3: case 4: case 6: case 7: case 8: case 10: case 12: case 14: case 15: case 16:
+      return true;
+    default:
+      return false;
+  }
+}
+
+// Will dc_score_grad take the thread-per-query kernel (tile I/O staged through shared memory, coalesced)?  Used by the
+// host-buffer entry point to decide between zero-copy access to pinned memory and staged copies.
+bool takes_thread_per_query_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel, const dc_supports& sv, int64_t batch) {
+  return sv.dtype == DC_F32 && fast_radial_kind(kernel) != KR_GENERIC && sv.n_class <= 4 && batch >= kTqMinBatch &&
+         tq_feature_count(fk_n_features(fk));
+}
+
 }  // namespace dc
 
 using namespace dc;

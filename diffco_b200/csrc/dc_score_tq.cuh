@@ -70,9 +70,12 @@ struct TqCfg {
   static constexpr int NG = (MODE == M_GRAD) ? 1 : 0;
   static constexpr int NRED = CW + NG * F;
   static constexpr int BAR_BYTES = round_up(NW * STAGES * 8, 128);
+  static constexpr int QS = QT * DC_MAX_DOF;      // staged configurations of the tile (per group)
+  static constexpr int GS = (CW + NG * F) * QT;   // reduced scores + feature gradients of the tile (per group)
+  // per-group scratch: NWG partial sums per reduced value, later re-used for the tile's output records [QT][C + D]
+  static constexpr int RED = QT * (NWG * NRED > CW + NG * DC_MAX_DOF ? NWG * NRED : CW + NG * DC_MAX_DOF);
   __host__ __device__ static constexpr size_t smem_bytes(int chunk_rows) {
-    return (size_t)BAR_BYTES +
-           sizeof(float) * ((size_t)NW * STAGES * chunk_rows * ROW + (size_t)NW * NRED * QT + (size_t)NGRP * (1 + NG) * F * QT);
+    return (size_t)BAR_BYTES + sizeof(float) * ((size_t)NW * STAGES * chunk_rows * ROW + (size_t)NGRP * (RED + F * QT + GS + QS));
   }
 };
 
@@ -96,9 +99,16 @@ __global__ void __launch_bounds__(512, 1) score_tq_kernel(const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * STAGES;
   T* ring_all = reinterpret_cast<T*>(smem_raw + Cfg::BAR_BYTES);
   T* ring = ring_all + (size_t)warp * STAGES * CH * ROW;
-  T* red = ring_all + (size_t)NW * STAGES * CH * ROW + (size_t)grp * NWG * NRED * QT;  // [wig][kk][QT]
-  T* xs = ring_all + (size_t)NW * STAGES * CH * ROW + (size_t)NW * NRED * QT + (size_t)grp * (1 + NG) * F * QT;  // [F][QT]
-  T* gs = xs + (size_t)F * QT;                                                                                    // [F][QT]
+  T* red = ring_all + (size_t)NW * STAGES * CH * ROW + (size_t)grp * Cfg::RED;  // [wig][kk][QT]
+  T* os = red;                                                                          // [QT][rec] after the reduction
+  T* xs = ring_all + (size_t)NW * STAGES * CH * ROW + (size_t)NGRP * Cfg::RED + (size_t)grp * (F * QT + Cfg::GS + Cfg::QS);
+  T* gs = xs + (size_t)F * QT;  // [CW + NG*F][QT]: reduced scores, then feature gradients
+  T* qs = gs + Cfg::GS;         // [QT][n_in]
+  // Output addressing.  `fused`: score and grad are the two halves of one [B, C+D] record buffer, so a tile's output is
+  // ONE contiguous block (what the all-gather ships, and what makes zero-copy writes to pinned host memory efficient).
+  const int n_out = a.n_class + (NG ? a.n_in : 0);
+  const bool fused = (NG == 0) ? (a.score_ld == a.n_class)
+                               : (a.jac_class < 0 && a.score_ld == a.grad_ld && a.score_ld == n_out && a.grad == a.score + a.n_class);
 
   // ---- this CTA's tiles (contiguous, balanced), dealt round-robin to its groups; this warp's slice of the supports
   const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
@@ -140,10 +150,22 @@ __global__ void __launch_bounds__(512, 1) score_tq_kernel(const __grid_constant_
     const long long b_base = tile * QT;
     const int nq = (int)min((long long)QT, a.batch - b_base);
 
-    // ---- phase A: FK, one query per thread, features into xs[f][t] ---------------------------------
+    // ---- phase A: stage the tile's configurations (coalesced; device or mapped host memory), then FK, one query per
+    //      thread, features into xs[f][t] ----------------------------------------------------------------------------
+    {
+      const T* src = a.q + (size_t)b_base * a.n_in;
+      const int n_words = nq * a.n_in;
+      if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        for (int i = gtid; i < n_words / 4; i += GT) reinterpret_cast<float4*>(qs)[i] = s4[i];
+      } else {
+        for (int i = gtid; i < n_words; i += GT) qs[i] = src[i];
+      }
+    }
+    group_barrier(bar_id, GT);
     if (gtid < QT) {
       if (gtid < nq) {
-        const T* qp = a.q + (size_t)(b_base + gtid) * a.n_in;
+        const T* qp = qs + gtid * a.n_in;
         if (a.fk.type == DC_FK_NONE) {
 #pragma unroll
           for (int f = 0; f < F; ++f) xs[f * QT + gtid] = qp[f];
@@ -271,26 +293,22 @@ __global__ void __launch_bounds__(512, 1) score_tq_kernel(const __grid_constant_
       T s = (T)0;
 #pragma unroll
       for (int w = 0; w < NWG; ++w) s += red[(w * NRED + kk) * QT + qi];
-      if (kk < CW) {
-        const long long b = b_base + qi;
-        if (kk < a.n_class && b < a.batch && a.write_score) a.score[(size_t)b * a.score_ld + kk] = s * a.rc.score_scale;
-      } else {
-        gs[(kk - CW) * QT + qi] = s * a.rc.grad_scale;
-      }
+      gs[idx] = s * (kk < CW ? a.rc.score_scale : a.rc.grad_scale);
     }
+    group_barrier(bar_id, GT);  // `red` is dead from here on: its storage becomes the output staging block `os`
 
-    // ---- phase C: J_FK^T g_x, one query per thread ---------------------------------------------------
-    if constexpr (MODE == M_GRAD) {
-      group_barrier(bar_id, GT);
-      if (gtid < nq) {
-        const long long b = b_base + gtid;
-        const T* qp = a.q + (size_t)b * a.n_in;
+    // ---- phase C: J_FK^T g_x, one query per thread, records into os[t][score | grad] ----------------------
+    if (gtid < nq) {
+      T* rec = os + gtid * n_out;
+      for (int c = 0; c < a.n_class; ++c) rec[c] = gs[c * QT + gtid];
+      if constexpr (MODE == M_GRAD) {
+        const T* qp = qs + gtid * a.n_in;
         T scale = (T)1;
-        if (CW == 1 && a.grad_out != nullptr) scale = a.grad_out[b];
-        T* out = a.grad + (size_t)b * a.grad_ld + (a.jac_class > 0 ? (size_t)a.jac_class * a.n_in : 0);
+        if (CW == 1 && a.grad_out != nullptr) scale = a.grad_out[b_base + gtid];
+        T* out = rec + a.n_class;
         if (a.fk.type == DC_FK_NONE) {
 #pragma unroll
-          for (int f = 0; f < F; ++f) out[f] = scale * gs[f * QT + gtid];
+          for (int f = 0; f < F; ++f) out[f] = scale * gs[(CW + f) * QT + gtid];
         } else {
           T qv[DC_MAX_DOF], gq[DC_MAX_DOF];
 #pragma unroll
@@ -298,12 +316,38 @@ __global__ void __launch_bounds__(512, 1) score_tq_kernel(const __grid_constant_
             qv[i] = (i < a.n_in) ? qp[i] : (T)0;
             gq[i] = (T)0;
           }
-          fk_vjp<T>(a.fk, qv, xs + gtid, QT, gs + gtid, QT, gq);
+          fk_vjp<T>(a.fk, qv, xs + gtid, QT, gs + CW * QT + gtid, QT, gq);
           for (int i = 0; i < a.n_in; ++i) out[i] = scale * gq[i];
         }
       }
     }
-    group_barrier(bar_id, GT);  // xs / gs / red are rewritten by the next tile
+    group_barrier(bar_id, GT);
+
+    // ---- write the tile out, coalesced -------------------------------------------------------------------
+    if (fused) {
+      T* dst = a.score + (size_t)b_base * n_out;
+      const int n_words = nq * n_out;
+      if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (int i = gtid; i < n_words / 4; i += GT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
+      } else {
+        for (int i = gtid; i < n_words; i += GT) dst[i] = os[i];
+      }
+    } else {
+      if (a.write_score) {
+        for (int i = gtid; i < nq * a.n_class; i += GT) {
+          const int t = i / a.n_class, c = i - t * a.n_class;
+          a.score[(size_t)(b_base + t) * a.score_ld + c] = os[t * n_out + c];
+        }
+      }
+      if constexpr (MODE == M_GRAD) {
+        T* gbase = a.grad + (a.jac_class > 0 ? (size_t)a.jac_class * a.n_in : 0);
+        for (int i = gtid; i < nq * a.n_in; i += GT) {
+          const int t = i / a.n_in, c = i - t * a.n_in;
+          gbase[(size_t)(b_base + t) * a.grad_ld + c] = os[t * n_out + a.n_class + c];
+        }
+      }
+    }
+    group_barrier(bar_id, GT);  // xs / gs / qs / red are rewritten by the next tile
   }
 }
 

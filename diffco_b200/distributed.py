@@ -61,6 +61,7 @@ class ShardedScorer:
         self._local_fn = local_fn
         self._buffers = {}
         self._pipe = None
+        self._q_stage = None
         if local_fn is None:
             self._sv, self._kfun = checker._select(weights)
             self._fk = checker._fk_for(self._sv)
@@ -120,23 +121,24 @@ class ShardedScorer:
         return buf[:total, :self.n_class], buf[:total, self.n_class:]
 
     # ---------------------------------------------------------------- host buffers in, host buffers out
-    def score_and_grad_host(self, q_host: torch.Tensor, out_host: torch.Tensor, chunks: int = 4) -> torch.Tensor:
+    def score_and_grad_host(self, q_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
         """End-to-end call for host-resident batches: ``q_host`` (b, D) and ``out_host`` (b, C+D) are (preferably pinned)
-        CPU tensors.  The batch is cut into ``chunks`` pieces that flow H2D -> fused kernel -> D2H on two side streams so
-        the PCIe copies overlap the compute of the neighbouring chunk.  With world > 1 the device-side result is also
-        all-gathered (every rank keeps the global batch on its GPU) before this rank's rows are copied back.
+        CPU tensors.  Single rank: ``dc_score_grad_host`` — chunks flow H2D -> fused kernel -> D2H on the pipeline's
+        streams so the PCIe copies overlap the compute.  With world > 1 the device-side result is also all-gathered (every
+        rank keeps the global batch on its GPU) before this rank's rows are copied back.
         Returns ``out_host`` once the work is enqueued; the caller synchronises the current stream."""
-        if self._pipe is None:
-            self._pipe = functional.HostPipeline(self.device)
+        if self._local_fn is not None:
+            raise RuntimeError("score_and_grad_host needs the CUDA scorer")
         b = q_host.shape[0]
         if self.world > 1:
-            cur = torch.cuda.current_stream(self.device)
-            qd = self._pipe.stage("q", (b, self.dof), self.dtype, 0)
+            if self._q_stage is None or self._q_stage.shape[0] < b:
+                self._q_stage = torch.empty((b, self.dof), dtype=self.dtype, device=self.device)
+            qd = self._q_stage[:b]
             qd.copy_(q_host, non_blocking=True)
             self.score_and_grad(qd)
             buf = self._buffer(self.world * b)
             out_host.copy_(buf[self.rank * b:(self.rank + 1) * b], non_blocking=True)
-            del cur
             return out_host
-        self._pipe.run(q_host, out_host, self._local, self.record_width, chunks)
-        return out_host
+        if self._pipe is None:
+            self._pipe = functional.HostPipeline(self.device)
+        return self._pipe.score_grad(self._fk, self._kfun.desc, self._sv, q_host, out_host, DC_GRAD_SUM)

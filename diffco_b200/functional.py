@@ -245,47 +245,42 @@ class _FkFunction(torch.autograd.Function):
 
 
 class HostPipeline:
-    """Chunked H2D -> kernel -> D2H pipeline over two side streams with persistent device staging buffers.
+    """Owner of a native ``dc_host_pipeline`` (include/diffco_b200.h): a few CUDA streams + device staging buffers through
+    which ``dc_score_grad_host`` pipelines H2D copy -> fused kernel -> D2H copy chunk by chunk.  The streams fork from and
+    join back into the caller's current stream, so events recorded there bracket all of the work and the call never
+    synchronises with the host."""
 
-    The side streams fork from and join back into the caller's current stream, so events recorded on the current
-    stream bracket all of the work and the call itself never synchronises with the host.
-    """
-
-    def __init__(self, device: torch.device, n_slots: int = 2):
+    def __init__(self, device: torch.device, chunk_rows: int = 16384, n_slots: int = 3):
         self.device = device
-        self.streams = [torch.cuda.Stream(device) for _ in range(n_slots)]
-        self._stage = {}
+        self.chunk_rows = chunk_rows
+        self._lib = _lib.load()
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self._lib.dc_host_pipeline_create(C.byref(handle), chunk_rows, n_slots), "dc_host_pipeline_create")
+        self._handle = handle
 
-    def stage(self, name: str, shape, dtype, slot: int) -> torch.Tensor:
-        key = (name, slot)
-        t = self._stage.get(key)
-        if t is None or t.dtype != dtype or t.shape[1:] != tuple(shape[1:]) or t.shape[0] < shape[0]:
-            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
-            self._stage[key] = t
-        return t[:shape[0]]
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None and h.value:
+            try:
+                self._lib.dc_host_pipeline_destroy(h)
+            except Exception:
+                pass
 
-    def run(self, q_host: torch.Tensor, out_host: torch.Tensor, local_fn, record_width: int, chunks: int) -> None:
-        b, d = q_host.shape
-        if out_host.shape != (b, record_width):
-            raise ValueError(f"out_host must have shape ({b}, {record_width}), got {tuple(out_host.shape)}")
-        if b == 0:
-            return
-        chunks = max(1, min(chunks, b))
-        per = -(-b // chunks)
-        cur = torch.cuda.current_stream(self.device)
-        for st in self.streams:
-            st.wait_stream(cur)
-        for i in range(chunks):
-            lo, hi = i * per, min(b, (i + 1) * per)
-            if hi <= lo:
-                break
-            slot = i % len(self.streams)
-            st = self.streams[slot]
-            with torch.cuda.stream(st):
-                qd = self.stage("q", (per, d), q_host.dtype, slot)[:hi - lo]
-                od = self.stage("o", (per, record_width), out_host.dtype, slot)[:hi - lo]
-                qd.copy_(q_host[lo:hi], non_blocking=True)
-                local_fn(qd, od)
-                out_host[lo:hi].copy_(od, non_blocking=True)
-        for st in self.streams:
-            cur.wait_stream(st)
+    def score_grad(self, fk: FkDesc, kernel: KernelDesc, sv: SupportSet, q_host: torch.Tensor, out_host: torch.Tensor,
+                   grad_mode: int = DC_GRAD_SUM) -> torch.Tensor:
+        """q_host (B, D), out_host (B, C [+ D]) contiguous CPU tensors of the model dtype (pinned for overlap)."""
+        if q_host.is_cuda or out_host.is_cuda:
+            raise ValueError("score_grad_host takes CPU tensors; use score_grad for device-resident batches")
+        B = q_host.shape[0]
+        rec = sv.n_class + (fk.dof if grad_mode == DC_GRAD_SUM else 0)
+        if q_host.dtype != sv.dtype or out_host.dtype != sv.dtype or not q_host.is_contiguous() or not out_host.is_contiguous():
+            raise ValueError(f"host buffers must be contiguous {sv.dtype} tensors")
+        if q_host.shape != (B, fk.dof) or out_host.shape != (B, rec):
+            raise ValueError(f"expected q_host ({B}, {fk.dof}) and out_host ({B}, {rec})")
+        if B:
+            with torch.cuda.device(self.device):
+                st = self._lib.dc_score_grad_host(self._handle, C.byref(fk), C.byref(kernel), C.byref(sv.desc), q_host.data_ptr(),
+                                                  B, out_host.data_ptr(), grad_mode, _stream_ptr(self.device))
+            _lib.check(st, "dc_score_grad_host")
+        return out_host

@@ -148,6 +148,19 @@ int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
                   int64_t batch, void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out,
                   int32_t grad_mode, dc_stream_t stream);
 
+/*
+ * Host buffers in, host buffers out (what a CPU-side caller such as the reference's optimisers or an evaluation grid
+ * holds): q_host[B,D] and out_host[B, C (+D with DC_GRAD_SUM)] = [score | grad] records are HOST pointers, ideally
+ * pinned.  The pipeline object owns a few streams and device staging buffers; the call cuts the batch into chunk_rows
+ * pieces that flow H2D -> dc_score_grad -> D2H on those streams (forked from and joined back into `stream`), overlapping
+ * the PCIe copies with the kernels, and returns without synchronising.  One pipeline per calling thread.
+ */
+typedef struct dc_host_pipeline dc_host_pipeline;
+int dc_host_pipeline_create(dc_host_pipeline** out, int64_t chunk_rows, int32_t n_slots);
+void dc_host_pipeline_destroy(dc_host_pipeline* pipeline);
+int dc_score_grad_host(dc_host_pipeline* pipeline, const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv,
+                       const void* q_host, int64_t batch, void* out_host, int32_t grad_mode, dc_stream_t stream);
+
 /* K[Na,Nb] = k(|xa_i - xb_j|^2) on pre-transformed features (training rows, fit_poly, jump-start block). */
 int dc_kernel_matrix(const dc_kernel_desc* kernel, const void* xa, int64_t na, const void* xb, int64_t nb,
                      int32_t n_features, int32_t dtype, void* k_out, dc_stream_t stream);

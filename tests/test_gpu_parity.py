@@ -643,7 +643,7 @@ def test_fused_record_output_and_host_pipeline(B, dev):
     assert torch.equal(s2, s1) and torch.equal(g2, g1)
     qh = q.float().pin_memory()
     oh = torch.empty(B, 8).pin_memory()
-    scorer.score_and_grad_host(qh, oh, chunks=3)
+    scorer.score_and_grad_host(qh, oh)
     torch.cuda.synchronize()
     assert rel(oh[:, :1], s_ref) <= 1e-5 and rel(oh[:, 1:], g_ref) <= 1e-5
     # DiffCo.score_and_grad: CPU in, CPU out

@@ -25,12 +25,13 @@ def lib():
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(dc_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:int|void|int64_t|const char\*)\s+(dc_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_header_declares_the_expected_entry_points():
     names = declared_functions()
-    for must in ("dc_score_grad", "dc_kernel_matrix", "dc_fk_forward", "dc_fk_vjp", "dc_perceptron_train", "dc_pack_supports"):
+    for must in ("dc_score_grad", "dc_kernel_matrix", "dc_fk_forward", "dc_fk_vjp", "dc_perceptron_train", "dc_pack_supports",
+                 "dc_score_grad_host", "dc_host_pipeline_create", "dc_host_pipeline_destroy"):
         assert must in names, names
 
 
