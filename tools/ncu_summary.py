@@ -44,7 +44,12 @@ def main():
     rows = list(csv.reader(io.StringIO(ncu(rep, "--page", "source", "--csv", "--print-source", "sass"))))
     hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) == len(hdr)]
+    body = rows[2:]
+    for n, r in enumerate(body):  # several captured launches: keep the first kernel's block only
+        if r and r[0] == "Kernel Name":
+            body = body[:n]
+            break
+    data = [r for r in body if len(r) == len(hdr)]
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
     with open(prefix + "_hot_sass.txt", "w") as f:
