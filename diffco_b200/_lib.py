@@ -20,6 +20,7 @@ DC_MAX_TOOL_POINTS = 2
 DC_MAX_FEATURES = 64
 DC_MAX_CLASSES = 8
 
+ABI_VERSION = 2
 DC_F32, DC_F64 = 0, 1
 DC_FK_NONE, DC_FK_PLANAR_CHAIN, DC_FK_SE2_BODY, DC_FK_SE3_BODY, DC_FK_DH_ARMS, DC_FK_SE2_BASE_PLANAR_ARM = range(6)
 DC_K_RQ, DC_K_POLYHARMONIC, DC_K_MULTIQUADRIC = 1, 2, 3
@@ -78,7 +79,13 @@ class Supports(C.Structure):
         ("row_stride", C.c_int32),
         ("dtype", C.c_int32),
         ("reserved", C.c_int32),
+        ("tc_blob", C.c_void_p),
+        ("tc_s2max", C.c_double),
     ]
+
+
+DC_OPT_TC_ENABLE, DC_OPT_TC_ERR_COEF, DC_OPT_TC_TOL_PAIR, DC_OPT_TC_MIN_BATCH = 1, 2, 3, 4
+KERNEL_NAMES = {0: "lane-split", 1: "thread-per-query", 2: "tensor-core", -1: "none"}
 
 
 # name -> (restype, argtypes); must list every function declared in include/diffco_b200.h
@@ -88,6 +95,11 @@ PROTOTYPES = {
     "dc_launch_count": (C.c_int64, []),
     "dc_supports_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dc_pack_supports": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_supports_tc_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "dc_pack_supports_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_set_option": (C.c_int, [C.c_int32, C.c_double]),
+    "dc_get_option": (C.c_double, [C.c_int32]),
+    "dc_last_score_kernel": (C.c_int, []),
     "dc_score_grad": (C.c_int, [C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "dc_host_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int32]),
@@ -124,8 +136,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, let it propagate
         fn.restype = res
         fn.argtypes = args
-    if lib.dc_abi_version() != 1:
-        raise NativeLibraryError(f"ABI version mismatch: library reports {lib.dc_abi_version()}, binding expects 1")
+    if lib.dc_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI version mismatch: library reports {lib.dc_abi_version()}, binding expects {ABI_VERSION}")
     _lib = lib
     return lib
 

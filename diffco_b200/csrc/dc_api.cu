@@ -11,6 +11,14 @@
 namespace dc {
 
 long long g_launch_count = 0;
+int g_last_score_kernel = -1;  // 0 lane-split, 1 thread-per-query, 2 tensor-core (dc_last_score_kernel)
+
+// dc_score_tc.cu
+bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel, const dc_supports& sv, int64_t batch,
+                              int grad_mode);
+int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q, int64_t batch,
+                  void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out, int32_t grad_mode,
+                  int num_sms, cudaStream_t stream);
 
 #define DC_TQ_DECL(name) int name(int n_feat, ScoreArgs<float>& a, int num_sms, cudaStream_t stream);
 DC_TQ_DECL(tq_rq2_c1_score)
@@ -221,6 +229,7 @@ static bool tq_feature_count(int f) {  // keep in sync with the switch in dc_sco
 // Will dc_score_grad take the thread-per-query kernel (tile I/O staged through shared memory, coalesced)?  Used by the
 // host-buffer entry point to decide between zero-copy access to pinned memory and staged copies.
 bool takes_thread_per_query_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel, const dc_supports& sv, int64_t batch) {
+  if (takes_tensor_core_kernel(fk, kernel, sv, batch, DC_GRAD_SUM)) return true;  // same staged, coalesced tile I/O
   return sv.dtype == DC_F32 && fast_radial_kind(kernel) != KR_GENERIC && sv.n_class <= 4 && batch >= kTqMinBatch &&
          tq_feature_count(fk_n_features(fk));
 }
@@ -245,6 +254,8 @@ const char* dc_status_string(int status) {
 }
 
 int64_t dc_launch_count(void) { return g_launch_count; }
+
+int dc_last_score_kernel(void) { return g_last_score_kernel; }
 
 int dc_supports_layout(int32_t n_features, int32_t n_class, int32_t dtype, int32_t* f_pad, int32_t* row_stride) {
   if (n_features < 1 || n_features > DC_MAX_FEATURES || n_class < 1 || n_class > DC_MAX_CLASSES) return DC_ERR_INVALID_ARG;
@@ -297,9 +308,20 @@ int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
   if (st != DC_OK) return st;
   cudaStream_t cs = (cudaStream_t)stream;
 
-  if (sv->dtype == DC_F64)
+  if (sv->dtype == DC_F64) {
+    g_last_score_kernel = 0;
     return score_grad_generic<double>(fk, kernel, sv, q, batch, score, score_ld, grad, grad_ld, grad_out, grad_mode, num_sms,
                                       cs);
+  }
+
+  // fp32, RQ(p = 2), one class, F <= 14, large batch, packed operand image present: tensor-core kernel
+  if (takes_tensor_core_kernel(*fk, *kernel, *sv, batch, grad_mode)) {
+    const int r = tc_score_grad(fk, kernel, sv, q, batch, score, score_ld, grad, grad_ld, grad_out, grad_mode, num_sms, cs);
+    if (r != DC_ERR_UNSUPPORTED) {
+      g_last_score_kernel = 2;
+      return r;
+    }
+  }
 
   // fp32: thread-per-query kernel for large batches of the instantiated shapes, lane-split kernel otherwise
   const int kind = fast_radial_kind(*kernel);
@@ -339,8 +361,12 @@ int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
     } else {
       r = fn(F, a, num_sms, cs);
     }
-    if (r != DC_ERR_UNSUPPORTED) return r;
+    if (r != DC_ERR_UNSUPPORTED) {
+      g_last_score_kernel = 1;
+      return r;
+    }
   }
+  g_last_score_kernel = 0;
   return score_grad_generic<float>(fk, kernel, sv, q, batch, score, score_ld, grad, grad_ld, grad_out, grad_mode, num_sms, cs);
 }
 

@@ -1,0 +1,120 @@
+// Tensor-core score kernel (dc_score_tc.cuh): instantiations, support-set packing entry points and the dispatch test.
+#include <cmath>
+#include <cstdlib>
+
+#include "dc_score_tc.cuh"
+
+namespace dc {
+
+// process-wide knobs (dc_set_option)
+static double g_tc_enable = -1.0;  // -1: not initialised (reads DIFFCO_B200_TC once)
+static double g_tc_err_coef = 5e-7;
+static double g_tc_tol_pair = 2e-7;
+static double g_tc_min_batch = 4096;
+
+static bool tc_enabled() {
+  if (g_tc_enable < 0) {
+    const char* e = std::getenv("DIFFCO_B200_TC");
+    g_tc_enable = (e != nullptr && e[0] == '0') ? 0.0 : 1.0;
+  }
+  return g_tc_enable > 0;
+}
+
+int tc_set_option(int option, double value) {
+  switch (option) {
+    case DC_OPT_TC_ENABLE: g_tc_enable = value != 0.0 ? 1.0 : 0.0; return DC_OK;
+    case DC_OPT_TC_ERR_COEF: if (!(value > 0)) return DC_ERR_INVALID_ARG; g_tc_err_coef = value; return DC_OK;
+    case DC_OPT_TC_TOL_PAIR: if (!(value > 0)) return DC_ERR_INVALID_ARG; g_tc_tol_pair = value; return DC_OK;
+    case DC_OPT_TC_MIN_BATCH: if (!(value >= 1)) return DC_ERR_INVALID_ARG; g_tc_min_batch = value; return DC_OK;
+    default: return DC_ERR_INVALID_ARG;
+  }
+}
+double tc_get_option(int option) {
+  switch (option) {
+    case DC_OPT_TC_ENABLE: return tc_enabled() ? 1.0 : 0.0;
+    case DC_OPT_TC_ERR_COEF: return g_tc_err_coef;
+    case DC_OPT_TC_TOL_PAIR: return g_tc_tol_pair;
+    case DC_OPT_TC_MIN_BATCH: return g_tc_min_batch;
+    default: return NAN;
+  }
+}
+
+static bool tc_shape_ok(int n_features, int n_class, int dtype) {
+  return dtype == DC_F32 && n_class == 1 && n_features >= 1 && n_features <= TcLayout::FMAX;
+}
+
+// Does dc_score_grad send this call to the tensor-core kernel?  (DiffCo.score with RQKernel(p = 2), one class,
+// F <= 14, fp32, score or score + summed gradient, a batch large enough to fill the SMs, and — when the caller told us
+// max|s|^2 — a kernel narrow enough that only a small fraction of the pairs falls under the near-pair threshold.)
+bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel, const dc_supports& sv, int64_t batch,
+                              int grad_mode) {
+  if (!tc_enabled() || sv.tc_blob == nullptr) return false;
+  const int F = fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim;
+  if (!tc_shape_ok(F, sv.n_class, sv.dtype) || fk.dof > DC_MAX_DOF) return false;
+  if (kernel.kind != DC_K_RQ || kernel.order != 2 || !(kernel.param > 0)) return false;
+  if (grad_mode != DC_GRAD_NONE && grad_mode != DC_GRAD_SUM) return false;
+  if (batch < (int64_t)g_tc_min_batch || sv.n >= (1 << 24)) return false;
+  if (sv.tc_s2max > 0) {
+    // near threshold on rho for a typical query (|x|^2 ~ max|s|^2 / 2) against the spread of the supports
+    const double drho = g_tc_err_coef * 1.5 * sv.tc_s2max;
+    const double tcrit = std::cbrt(std::fmax(kernel.param * drho / g_tc_tol_pair, 1.0));
+    const double thr = (tcrit - 1.0) / (kernel.param / 2.0);
+    if (thr > 0.04 * sv.tc_s2max) return false;
+  }
+  return true;
+}
+
+int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q, int64_t batch,
+                  void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out, int32_t grad_mode,
+                  int num_sms, cudaStream_t stream) {
+  TcArgs a;
+  a.fk = *fk;
+  if (!make_radial_consts<float>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
+  a.blob = static_cast<const unsigned char*>(sv->tc_blob);
+  a.table = static_cast<const float*>(sv->table);
+  a.q = static_cast<const float*>(q);
+  a.score = static_cast<float*>(score);
+  a.grad = static_cast<float*>(grad);
+  a.grad_out = (grad_mode == DC_GRAD_SUM) ? static_cast<const float*>(grad_out) : nullptr;
+  a.trace = nullptr;
+  a.dbg = nullptr;
+  a.batch = batch;
+  a.score_ld = score_ld;
+  a.grad_ld = grad_ld;
+  a.n_sv = (int)sv->n;
+  a.n_feat = sv->n_features;
+  a.n_in = fk->dof;
+  a.row_stride = sv->row_stride;
+  a.f_pad = sv->f_pad;
+  a.n_tiles = 0;
+  a.n_chunks = 0;
+  a.err_coef = (float)g_tc_err_coef;
+  a.tol_pair = (float)g_tc_tol_pair;
+  return grad_mode == DC_GRAD_NONE ? launch_score_tc<TC_SCORE>(a, num_sms, stream)
+                                   : launch_score_tc<TC_GRAD>(a, num_sms, stream);
+}
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" {
+
+int dc_supports_tc_bytes(int64_t n, int32_t n_features, int32_t n_class, int32_t dtype, int64_t* bytes) {
+  if (n < 1 || !bytes) return DC_ERR_INVALID_ARG;
+  if (!tc_shape_ok(n_features, n_class, dtype) || n >= (1 << 24)) return DC_ERR_UNSUPPORTED;
+  *bytes = (int64_t)tc_blob_bytes(n);
+  return DC_OK;
+}
+
+int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_features, void* blob, dc_stream_t stream) {
+  if (n < 1 || !s_feat || !w || !blob || (reinterpret_cast<uintptr_t>(blob) & 127) != 0) return DC_ERR_INVALID_ARG;
+  if (!tc_shape_ok(n_features, 1, DC_F32) || n >= (1 << 24)) return DC_ERR_UNSUPPORTED;
+  return launch_pack_supports_tc(static_cast<const float*>(s_feat), static_cast<const float*>(w), n, n_features,
+                                 static_cast<unsigned char*>(blob), (cudaStream_t)stream);
+}
+
+int dc_set_option(int32_t option, double value) { return tc_set_option(option, value); }
+double dc_get_option(int32_t option) { return tc_get_option(option); }
+
+}  // extern "C"

@@ -80,7 +80,20 @@ class SupportSet:
                                             self.table.data_ptr(), _stream_ptr(device)), "dc_pack_supports")
         self.dtype = dtype
         self.device = device
-        self.desc = Supports(self.table.data_ptr(), self.n, self.n_features, self.n_class, f_pad.value, row.value, code, 0)
+        # Optional tensor-core operand image (fp32, one class, F <= 14): lets dc_score_grad run DiffCo.score with
+        # RQKernel(p = 2) on tcgen05 tensor cores (csrc/dc_score_tc.cuh).  max|s|^2 is read back once here (pack time).
+        self.tc_blob = None
+        tc_ptr, s2max = None, 0.0
+        nbytes = C.c_int64()
+        if lib.dc_supports_tc_bytes(self.n, self.n_features, self.n_class, code, C.byref(nbytes)) == 0:
+            self.tc_blob = torch.empty(nbytes.value + 128, dtype=torch.uint8, device=device)
+            tc_ptr = (self.tc_blob.data_ptr() + 127) // 128 * 128
+            with torch.cuda.device(device):
+                _lib.check(lib.dc_pack_supports_tc(s.data_ptr(), w.data_ptr(), self.n, self.n_features, tc_ptr,
+                                                   _stream_ptr(device)), "dc_pack_supports_tc")
+            s2max = float(s.double().square().sum(dim=1).max().item())
+        self.desc = Supports(self.table.data_ptr(), self.n, self.n_features, self.n_class, f_pad.value, row.value, code, 0,
+                             tc_ptr, s2max)
 
 
 def score_grad(fk: FkDesc, kernel: KernelDesc, sv: SupportSet, q: torch.Tensor, grad_mode: int = DC_GRAD_NONE,

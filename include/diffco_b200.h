@@ -14,11 +14,13 @@
  *                         kernel_func(S, novel)      diffco/kernel_perceptrons.py:246 (jump start)
  *   dc_fk_forward/vjp  <- *.fkine                    diffco/model.py:40-48,90-93,156-159,225-241,366-383,430-453,486-503
  *   dc_perceptron_train<- DiffCo.train_perceptron    diffco/kernel_perceptrons.py:98-158
+ *   dc_pack_supports_tc<- (none)  optional tensor-core operand image of the support set: with it, dc_score_grad runs
+ *                         DiffCo.score (RQKernel p = 2, one class, F <= 14, fp32) on tcgen05 tensor cores
  *
  * Conventions: all pointers except descriptors are DEVICE pointers to row-major contiguous arrays of `dtype`
  * (DC_F32 / DC_F64); descriptors are plain-old-data structs in HOST memory, copied by value into the launch.
  * Every call enqueues work on `stream` and returns without synchronising; return value 0 = ok, <0 = dc_status.
- * No torch types, no exceptions, no global state.
+ * No torch types, no exceptions; the only process-wide state is the launch counter and the dc_set_option knobs.
  */
 #ifndef DIFFCO_B200_H
 #define DIFFCO_B200_H
@@ -29,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 1
+#define DC_ABI_VERSION 2
 
 #define DC_MAX_DOF 16
 #define DC_MAX_LINKS 16
@@ -117,6 +119,9 @@ typedef struct dc_supports {
   int32_t row_stride;  /* elements per row */
   int32_t dtype;
   int32_t reserved;
+  const void* tc_blob; /* device, optional (NULL = none): image written by dc_pack_supports_tc for the same S_feat / W */
+  double tc_s2max;     /* max_n |s_n|^2 if known (> 0): lets dc_score_grad skip the tensor-core path when the kernel
+                          width makes too many pairs "near" (they are re-evaluated exactly on the FP32 pipe); 0 = unknown */
 } dc_supports;
 
 typedef enum dc_grad_mode {
@@ -135,6 +140,26 @@ int dc_supports_layout(int32_t n_features, int32_t n_class, int32_t dtype, int32
 /* Pack S_feat[N,F] (= support_transformed.reshape(N,-1)) and W[N,C] (gains or rbf_nodes) into `table`. */
 int dc_pack_supports(const void* s_feat, const void* w, int64_t n, int32_t n_features, int32_t n_class, int32_t dtype,
                      void* table, dc_stream_t stream);
+
+/*
+ * Tensor-core operand image of a support set (fp32, one class, n_features <= 14): dc_supports_tc_bytes gives the
+ * buffer size (DC_ERR_UNSUPPORTED for shapes the tensor-core kernel does not cover), dc_pack_supports_tc fills a
+ * 128-byte aligned device buffer from S_feat[N,F] and W[N].  Put the pointer into dc_supports.tc_blob.
+ */
+int dc_supports_tc_bytes(int64_t n, int32_t n_features, int32_t n_class, int32_t dtype, int64_t* bytes);
+int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_features, void* blob, dc_stream_t stream);
+
+/* Process-wide tuning knobs (the only global state of the library besides the launch counter). */
+typedef enum dc_option {
+  DC_OPT_TC_ENABLE = 1,   /* 0 / 1 (default 1; environment DIFFCO_B200_TC=0 also disables): use the tensor-core kernel */
+  DC_OPT_TC_ERR_COEF = 2, /* bound on the error of the tensor-core rho, relative to |x|^2 + max|s|^2 (default 5e-7)     */
+  DC_OPT_TC_TOL_PAIR = 3, /* admissible error of one pair's kernel value (default 2e-7): sets the near-pair threshold   */
+  DC_OPT_TC_MIN_BATCH = 4 /* smallest batch sent to the tensor-core kernel (default 4096)                               */
+} dc_option;
+int dc_set_option(int32_t option, double value);
+double dc_get_option(int32_t option);
+/* Which kernel the last dc_score_grad call of this process launched: 0 lane-split, 1 thread-per-query, 2 tensor-core. */
+int dc_last_score_kernel(void);
 
 /*
  * The hot path.  score[B,C] = sum_n w[n,c] k(|FK(q_b) - s_n|^2) and, per grad_mode, its gradient w.r.t. q.

@@ -25,7 +25,7 @@ def lib():
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:int|void|int64_t|const char\*)\s+(dc_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:int|void|int64_t|double|const char\*)\s+(dc_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_header_declares_the_expected_entry_points():

@@ -6,18 +6,10 @@
 namespace dc { long long g_launch_count = 0; }
 using namespace dc;
 
-__device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t at, uint64_t bd, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(at), "l"(bd), "r"(idesc), "r"(acc) : "memory");
-}
-__host__ __device__ constexpr uint32_t idesc_f16(int n) {  // D=F32, A=B=F16, K-major, M=128
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
+__host__ __device__ constexpr uint32_t idesc_f16(int n) { return umma_idesc_f16(n); }
 
 // kind: 0 tf32, 1 f16.  ts: A from TMEM.  nacc: accumulators rotated.  reps: MMAs issued.
-__global__ void __launch_bounds__(128, 1) bench(int kind, int n, int ts, int nacc, int reps, long long* out) {
+__global__ void __launch_bounds__(128, 2) bench(int kind, int n, int ts, int nacc, int reps, long long* out) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 64);
@@ -26,7 +18,7 @@ __global__ void __launch_bounds__(128, 1) bench(int kind, int n, int ts, int nac
   if (threadIdx.x < 32) {
     if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncwarp();
-    tmem_alloc(slot, 512);
+    tmem_alloc(slot, 256);
   }
   fence_proxy_async();
   tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -38,14 +30,14 @@ __global__ void __launch_bounds__(128, 1) bench(int kind, int n, int ts, int nac
     const uint32_t id = kind == 0 ? umma_idesc_tf32(n) : idesc_f16(n);
     const int astride = n <= 64 ? 64 : (n <= 128 ? 128 : 256);   // accumulator column stride
     uint32_t parity = 0;
-    for (int rep = 0; rep < 3; ++rep) {
+    for (int rep = 0; rep < 1; ++rep) {
       const long long t0 = clock64();
       if (elect_one()) {
 #pragma unroll 4
         for (int i = 0; i < reps; ++i) {
           const uint32_t d = tmem + (uint32_t)((i & (nacc - 1)) * astride);
-          if (kind == 0) { if (ts) umma_ts(d, tmem + 448, bd, id, 1u); else umma_ss(d, ad, bd, id, 1u); }
-          else           { if (ts) umma_f16_ts(d, tmem + 448, bd, id, 1u); else umma_f16_ss(d, ad, bd, id, 1u); }
+          if (kind == 0) { if (ts) umma_ts(d, tmem + 224, bd, id, 1u); else umma_ss(d, ad, bd, id, 1u); }
+          else           { if (ts) umma_f16_ts(d, tmem + 224, bd, id, 1u); else umma_f16_ss(d, ad, bd, id, 1u); }
         }
       }
       __syncwarp();
@@ -54,11 +46,11 @@ __global__ void __launch_bounds__(128, 1) bench(int kind, int n, int ts, int nac
       __syncwarp();
       mbar_wait_wd(bar, parity); parity ^= 1;
       const long long t2 = clock64();
-      if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+      if (threadIdx.x == 0) { atomicMax((unsigned long long*)&out[0], (unsigned long long)(t1 - t0)); atomicMax((unsigned long long*)&out[1], (unsigned long long)(t2 - t0)); }
     }
   }
   tc_fence_before(); __syncthreads();
-  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 int main() {
@@ -67,15 +59,18 @@ int main() {
   const int reps = 64;
   printf("kind  N  A    nacc   issue cyc/MMA   total cyc/MMA\n");
   for (int kind = 0; kind < 2; ++kind)
-    for (int n : {16, 32, 48, 96, 128, 256})
+    for (int n : {32, 96})
       for (int ts = 0; ts < 2; ++ts)
-        for (int nacc : {1, 2, 4}) {
-          if (nacc * (n <= 64 ? 64 : (n <= 128 ? 128 : 256)) > 448) continue;
-          bench<<<1, 128, 128 + 65536 + 32768>>>(kind, n, ts, nacc, reps, d_out);
+        for (int nacc : {1}) {
+          if (nacc * (n <= 64 ? 64 : (n <= 128 ? 128 : 256)) > 224) continue;
+         for (int grid : {1, 296}) {
+          cudaMemset(d_out, 0, 16);
+          bench<<<grid, 128, 128 + 65536 + 32768>>>(kind, n, ts, nacc, reps, d_out);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
           long long h[2]; cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
-          printf("%s %4d  %s  %d   %8.1f   %8.1f\n", kind ? "f16 " : "tf32", n, ts ? "tmem" : "smem", nacc, (double)h[0] / reps, (double)h[1] / reps);
+          printf("%s %4d  %s  %d  grid %3d  %8.1f   %8.1f\n", kind ? "f16 " : "tf32", n, ts ? "tmem" : "smem", nacc, grid, (double)h[0] / reps, (double)h[1] / reps);
+         }
         }
   return 0;
 }
