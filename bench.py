@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="configurations per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc", type=int, default=1, choices=[0, 1],
+                    help="1: tensor-core kernel (default); 0: force the FP32-pipe thread-per-query kernel")
     return ap.parse_args()
 
 
@@ -232,6 +234,7 @@ def run_native(args):
     from diffco_b200 import model as M
 
     lib = _lib.load()
+    _lib.check(lib.dc_set_option(_lib.DC_OPT_TC_ENABLE, float(args.tc)), "dc_set_option")
     B = args.batch
     S, w, q = make_problem(rank, B)
     robot = M.RevolutePlanarRobot(1.0, 0.3, dof=DOF)
@@ -296,16 +299,21 @@ def run_native(args):
 
     ms_k, k_launches, _, _ = timed(step_kernel, args.steps, 3)
     per_launch_s = ms_k * 1e-3 / max(1, k_launches)
+    which = lib.dc_last_score_kernel()
+    kernel_name = {2: "score_tc_kernel<GRAD> (tcgen05 kind::f16, TMEM, bulk TMA; RQ2, C=1, F=14)",
+                   1: "score_tq_kernel<F=14,RQ2,C=1,GRAD> (FP32 pipe, bulk TMA)"}.get(which, _lib.KERNEL_NAMES.get(which, "?"))
     hbm_peak, peak_src, sm_max = load_peaks()
     achieved_gbs = BYTES_PER_EVAL * B / per_launch_s / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get("tensor-core" if which == 2 else "thread-per-query", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     fp32_peak_tflops = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     achieved_tflops = FLOPS_PER_EVAL * B / per_launch_s / 1e12
+    # the unit that bounds the tensor-core kernel: one MUFU reciprocal per (query, support) pair, 16 per clock per SM
+    pairs_per_clk_sm = B * N_SV / per_launch_s / (148 * sm_max * 1e6)
 
     # ---- end to end through the host-buffer API (`e2e`) -----------------------------------------------------
     def step_e2e():
@@ -332,13 +340,19 @@ def run_native(args):
                        "l2": "flushed before every step (256 MiB memset, untimed); per-step CUDA events summed"},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "score_tq_kernel<FP=7,RQ2,C=1,GRAD>", "kernel_ms": per_launch_s * 1e3,
+                         "kernel": kernel_name, "kernel_ms": per_launch_s * 1e3,
                          "algorithmic_bytes_per_launch": BYTES_PER_EVAL * B,
-                         "note": "the path is FP32-pipe bound (2600 flop/B), not HBM bound: see roofline_fp32"},
-            "roofline_fp32": {"bound": "fp32_fma_pipe", "achieved": achieved_tflops, "peak": fp32_peak_tflops,
-                              "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
-                              "peak_source": f"148 SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (nominal max clock)",
-                              "algorithmic_flops_per_launch": FLOPS_PER_EVAL * B},
+                         "note": "the path is compute bound (2600 flop/B), not HBM bound: see roofline_compute"},
+            "roofline_compute": ({"bound": "mufu (one reciprocal per query-support pair; contractions on tcgen05)",
+                                  "achieved": pairs_per_clk_sm, "peak": 16.0, "unit": "pairs/clk/SM",
+                                  "frac": pairs_per_clk_sm / 16.0,
+                                  "peak_source": f"16 MUFU lanes per SM at {sm_max:.0f} MHz (nominal max clock)",
+                                  "algorithmic_tflops": achieved_tflops,
+                                  "fp32_fma_pipe_peak_tflops": fp32_peak_tflops} if which == 2 else
+                                 {"bound": "fp32_fma_pipe", "achieved": achieved_tflops, "peak": fp32_peak_tflops,
+                                  "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
+                                  "peak_source": f"148 SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (nominal max clock)",
+                                  "algorithmic_flops_per_launch": FLOPS_PER_EVAL * B}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": q_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
