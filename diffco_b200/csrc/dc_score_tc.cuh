@@ -326,10 +326,11 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
 
 #ifdef DC_TC_ENABLE_TRACE
 #define DC_TC_TRACE(slot, gidx) \
-  do { if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && (gidx) < 64) a.trace[(gidx) * 16 + (slot)] = clock64(); } while (0)
+  do { if (a.trace != nullptr && blockIdx.x == 1 && lane == 0 && (gidx) < 64) a.trace[(gidx) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define DC_TC_TRACE(slot, gidx) do { } while (0)
 #endif
+#define DC_TC_TRACE_TILE(ev) do { if (warp == 0) DC_TC_TRACE((int)(t - t0), 50 + (ev)); } while (0)
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
 enum TcMode { TC_SCORE = 0, TC_GRAD = 1 };
@@ -534,6 +535,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
       const long long b_base = t * L::TM;
       const int nq = (int)min((long long)L::TM, a.batch - b_base);
       // ---- stage the tile's configurations (coalesced), FK, A operand ----------------------------------------
+      DC_TC_TRACE_TILE(0);
       {
         const float* src = a.q + (size_t)b_base * a.n_in;
         const int n_words = nq * a.n_in;
@@ -618,7 +620,9 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         const float tcrit = cbrtf(fmaxf(-a.rc.grad_scale * 0.5f * drho / a.tol_pair, 1.f));  // (gamma drho / tol)^(1/3)
         thr_s[row] = in_range ? sx * sx * (tcrit - 1.f) / a.rc.c0 : 3.0e38f;
       }
+      DC_TC_TRACE_TILE(1);
       asm volatile("bar.sync 1, 256;" ::: "memory");  // xs, thr_s visible; qs free for the output records
+      DC_TC_TRACE_TILE(2);
       const float thr = thr_s[row];
 
       P2 sc2(0.f, 0.f);
@@ -709,12 +713,15 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         if (warp == 0) DC_TC_TRACE(13, g);
         mbar_arrive(&bar_cc[st]);
       }
+      DC_TC_TRACE_TILE(3);
       if (qcount > 0) {
         __syncwarp();
         tc_drain_pairs(a, queue, qcount, xs, gacc_w, sacc_w, lane);
       }
+      DC_TC_TRACE_TILE(4);
       if (!owner) sc_p[row] = sc2.lo() + sc2.hi();
       asm volatile("bar.sync 1, 256;" ::: "memory");  // exact terms and second-half partial scores are complete
+      DC_TC_TRACE_TILE(5);
 
       // ---- epilogue (row owners): G from TMEM, feature gradient, J_FK^T, records into shared memory -----------------
       if (owner) {
@@ -771,7 +778,9 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         // the accumulator must not be overwritten by the next tile's first GEMM2 before the owners have read it: the
         // owners' wait on bar_g above orders that (their next arrival on bar_cc comes after this epilogue)
       }
+      DC_TC_TRACE_TILE(6);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      DC_TC_TRACE_TILE(7);
       if (fused) {
         float* dst = a.score + (size_t)b_base * n_out;
         const int n_words = nq * n_out;
@@ -790,6 +799,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // qs / os are rewritten by the next tile
+      DC_TC_TRACE_TILE(8);
     }
   }
 

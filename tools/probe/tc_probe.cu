@@ -139,6 +139,8 @@ int main(int argc, char** argv) {
       for (int k : {8, 9, 10, 11, 12, 13}) printf(" %6lld", tr[g * 16 + k] ? tr[g * 16 + k] - b0 : -1);
       printf("\n");
     }
+    printf("tile events (cycles rel. to chunk-0 start of tile 0): start, fk done, bar, loop end, drained, bar, epilogue done, bar, copied\n");
+    for (int ti = 0; ti < 3; ++ti) { printf("tile %d:", ti); for (int ev = 0; ev < 9; ++ev) printf(" %7lld", tr[(50 + ev) * 16 + ti] ? tr[(50 + ev) * 16 + ti] - b0 : -1); printf("\n"); }
     a.trace = nullptr;
   }
   // ---- timing ------------------------------------------------------------------------------------------------
