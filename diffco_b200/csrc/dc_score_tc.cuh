@@ -71,7 +71,7 @@ struct TcLayout {
   static constexpr int QWARPS = 8;                             // query warps: 4 TMEM lane quarters x 2 column halves
   static constexpr int QTHREADS = QWARPS * 32;
   static constexpr int CTRL_WARP = QWARPS;
-  static constexpr int THREADS = QTHREADS + 32;
+  static constexpr int THREADS = QTHREADS + 128;  // + the control warpgroup: warp 8 works, warps 9..11 only donate registers
   static constexpr int SM_XS = SM_A + TM * K1 * 2;             // features of the tile [128][16] f32 (near-pair path)
   // one region, three lives per tile: staged q [128][16] -> per-warp exact accumulators (feature gradient
   // [8][32][16] + score [8][32]) -> output records [128][17]
@@ -436,9 +436,12 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == L::CTRL_WARP) {
-    // ================= control warp: TMA producer + MMA issuer (one elected lane issues) ========================
-    if (total > 0) {
+  // Register reallocation between the warpgroups (setmaxnreg): the kernel is launched with 80 registers per thread
+  // (12 warps x 2 CTAs per SM); the control warpgroup keeps 32 and the two query warpgroups grow to 104 (32 x 128 + 104 x 256 = the CTA's pool).
+  if (warp >= L::CTRL_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+    // ================= control warp: TMA producer + MMA issuer (one elected lane issues); warps 9..11 idle =========
+    if (warp == L::CTRL_WARP && total > 0) {
       constexpr uint32_t idesc1 = umma_idesc_f16(NC);
       constexpr uint32_t idesc2 = umma_idesc_f16(L::N2);
       const uint32_t a_s = smem_u32(a_op);
@@ -515,10 +518,13 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
     // ================= query threads: row = 32 (warp & 3) + lane, column half = warp >> 2 ==========================
     const int row = ((warp & 3) << 5) | lane;
     const int hcol = warp >> 2;
-    const bool owner = hcol == 0;  // owners run FK, the A operand and the epilogue of their row
+    // owners run FK, the A operand and the epilogue of their row: the higher-numbered half, which the warp scheduler
+    // favours — those phases are the CTA's critical path (the other half waits at the barriers)
+    const bool owner = hcol == 1;
     const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t* queue = queues + warp * L::QCAP;
     float* gacc_w = gacc + warp * 32 * 16;
@@ -664,7 +670,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
             for (int c = 0; c < 16; ++c) {
               const bool near = __uint_as_float(rb[c]) < thr;
               nearmask |= near ? (1u << c) : 0u;
-              rb[c] = near ? 0x7f000000u : rb[c];  // 1.7e38 -> u = 0: the pair leaves the tensor-core sums
+              rb[c] = near ? 0x5d000000u : rb[c];  // 5.8e17 -> u ~ 1e-18 (and t0 t1 stays finite): the pair leaves the sums
             }
             const int n0 = j * NC + hcol * (NC / 2) + col0;
             uint32_t todo = __reduce_or_sync(0xffffffffu, nearmask);  // columns some lane of the warp flagged
@@ -692,7 +698,8 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
             const float2 w2 = *reinterpret_cast<const float2*>(wsm + col0 + c);
             const P2 rho2(__uint_as_float(rb[c]), __uint_as_float(rb[c + 1]));
             const P2 tt = pfma_bb(rho2, c0s, 1.0f);
-            const P2 u(fast_rcp(tt.lo()), fast_rcp(tt.hi()));
+            const float rr = fast_rcp(tt.lo() * tt.hi());  // one MUFU per column pair: 1/t0 = t1 / (t0 t1)
+            const P2 u = pmul_b(P2(tt.hi(), tt.lo()), rr);
             const P2 k = pmul(u, u);
             const P2 wk = pmul(P2(w2), k);
             sc2 = padd(sc2, wk);
@@ -750,13 +757,13 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
 #pragma unroll
           for (int f = 0; f < FM; ++f) {
             const float gsum = (__uint_as_float(gm[f]) + __uint_as_float(gc[f])) * inv_sx;  // sum cc' s
-            const float gex = gacc_w[lane * 16 + f] + gacc_w[4 * 32 * 16 + lane * 16 + f];  // column halves 0 + 1
+            const float gex = gacc_w[lane * 16 + f - 4 * 32 * 16] + gacc_w[lane * 16 + f];  // column halves 0 + 1
             gx[f] = a.rc.grad_scale * (fmaf(xl[f], csum, -gsum) * inv_sw + gex);
           }
         }
         tc_fence_before();
         const float score =
-            a.rc.score_scale * ((sc2.lo() + sc2.hi() + sc_p[row]) * inv_sw + (sacc_w[lane] + sacc_w[4 * 32 + lane]));
+            a.rc.score_scale * ((sc_p[row] + (sc2.lo() + sc2.hi())) * inv_sw + (sacc_w[lane - 4 * 32] + sacc_w[lane]));
         asm volatile("bar.sync 2, 128;" ::: "memory");  // every owner has read its accumulators: the region becomes `os`
         if (row < nq) {
           float* rec = os + row * n_out;
