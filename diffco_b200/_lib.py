@@ -84,6 +84,16 @@ class Supports(C.Structure):
     ]
 
 
+class TrajParams(C.Structure):
+    _fields_ = [
+        ("dif_weight", C.c_double), ("max_move_weight", C.c_double), ("collision_weight", C.c_double),
+        ("joint_limit_weight", C.c_double), ("safety_bias", C.c_double), ("max_speed", C.c_double),
+        ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+        ("limits", (C.c_double * 2) * DC_MAX_DOF),
+        ("wrap", C.c_int32 * DC_MAX_DOF),
+    ]
+
+
 DC_OPT_TC_ENABLE, DC_OPT_TC_ERR_COEF, DC_OPT_TC_TOL_PAIR, DC_OPT_TC_MIN_BATCH = 1, 2, 3, 4
 KERNEL_NAMES = {0: "lane-split", 1: "thread-per-query", 2: "tensor-core", -1: "none"}
 
@@ -112,6 +122,8 @@ PROTOTYPES = {
     "dc_perceptron_train": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
+    "dc_traj_step": (C.c_int, [C.POINTER(FkDesc), C.POINTER(TrajParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dc_fk_vjp": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -7,9 +7,10 @@ import.  ``dist_est`` is any callable with the protocol of SURVEY.md §8b — no
 Jacobian behind autograd.  The optimisation drivers themselves are host logic (Adam / scipy SLSQP over ~20 waypoints);
 what they spend their time in — dist_est and robot.fkine with gradients — runs on the GPU.
 
-``Weighted.step`` additionally has a device-resident fast path (``options['fused'] = True``): the whole penalty
-(collision hinge + max-move + joint-limit + path length) and its gradient come from ONE launch of ``dc_traj_cost_grad``
-per step and the Adam update from a second, both captured in a CUDA graph.
+``Weighted.step`` additionally has a device-resident fast path (``options['fused'] = True``, diffco_b200/trajopt.py): the
+penalty (collision hinge + max-move + joint-limit + path length) and its gradient are assembled analytically from
+``dc_score_grad`` / ``dc_fk_forward`` / ``dc_fk_vjp`` launches plus a dozen element-wise ops, and the whole step including
+the Adam update is ONE CUDA graph replayed per iteration.
 
 Not provided: ``trustconstr_traj_optimize`` (needs second derivatives of dist_est; optim.py:380-391) and
 ``gradient_free_traj_optimize`` — both raise NotImplementedError rather than silently doing something else.
@@ -303,7 +304,7 @@ class Weighted(TrajOptimizer):
         if self.fused:
             from . import trajopt
 
-            p, history = trajopt.fused_weighted_steps(self, p, maxiter, mask)
+            p, history = trajopt.fused_weighted_steps(self, p, maxiter, mask, verbose)
         else:
             p, history = self._autograd_steps(p, maxiter, mask, verbose)
         out = self.normalizer(p.detach().cpu())

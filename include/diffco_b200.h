@@ -14,6 +14,7 @@
  *                         kernel_func(S, novel)      diffco/kernel_perceptrons.py:246 (jump start)
  *   dc_fk_forward/vjp  <- *.fkine                    diffco/model.py:40-48,90-93,156-159,225-241,366-383,430-453,486-503
  *   dc_perceptron_train<- DiffCo.train_perceptron    diffco/kernel_perceptrons.py:98-158
+ *   dc_traj_step       <- Weighted.step iteration   diffco/optim.py:706-752 (penalty, its gradient, Adam, wrap)
  *   dc_pack_supports_tc<- (none)  optional tensor-core operand image of the support set: with it, dc_score_grad runs
  *                         DiffCo.score (RQKernel p = 2, one class, F <= 14, fp32) on tcgen05 tensor cores
  *
@@ -206,6 +207,25 @@ int dc_fk_vjp(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype,
 int dc_perceptron_train(const dc_kernel_desc* kernel, const void* x_feat, const void* y, int64_t n, int32_t n_features,
                         int32_t n_class, int32_t dtype, double beta, int64_t max_iteration, void* gains, void* hypothesis,
                         void* kernel_matrix, void* diag, int32_t legacy_multi, int64_t* iterations_out, dc_stream_t stream);
+
+/*
+ * One iteration of the reference's penalty trajectory optimiser (Weighted.step, diffco/optim.py:706-752; the same terms
+ * as adam_traj_optimize, optim.py:86-127) for W waypoints in one launch: control points, path length, max-move and
+ * joint-limit hinges, the collision hinge on `score` (+ `score_grad` = d score/dp from dc_score_grad; both NULL = no
+ * collision term), the analytic gradient of the weighted sum, the `mask` multipliers, torch.optim.Adam's update and
+ * robot.wrap.  p[W,dof], exp_avg, exp_avg_sq are IN/OUT device arrays of `dtype`; `step` is the optimiser's step count
+ * (device double, incremented); terms[5] receives {path length, collision, joint limit, max move, constraint loss}.
+ */
+typedef struct dc_traj_params {
+  double dif_weight, max_move_weight, collision_weight, joint_limit_weight; /* optim.py:19-22,669-676 */
+  double safety_bias, max_speed;
+  double lr, beta1, beta2, eps;          /* torch.optim.Adam */
+  double limits[DC_MAX_DOF][2];          /* robot.limits */
+  int32_t wrap[DC_MAX_DOF];              /* 1: wrap this coordinate to [-pi, pi) after the update (robot.wrap) */
+} dc_traj_params;
+int dc_traj_step(const dc_fk_desc* fk, const dc_traj_params* params, int64_t n_waypoints, int32_t dtype, void* p,
+                 const void* score, const void* score_grad, const void* mask, void* exp_avg, void* exp_avg_sq, double* step,
+                 void* terms, dc_stream_t stream);
 
 #ifdef __cplusplus
 }

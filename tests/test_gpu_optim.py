@@ -84,3 +84,55 @@ def test_weighted_step_device_resident(problem):
         if float((10 * col + 10 * mm + 10 * jl).detach()) <= 0.5:
             break
     assert P.rel_to_max(res.x, p.detach()) <= 1e-5
+
+
+def test_weighted_step_graphed_matches_autograd_path(problem):
+    """options['fused'] = True (diffco_b200/trajopt.py): the analytic, CUDA-graph-replayed step must walk the same
+    trajectory as the autograd step of the reference's Weighted.step (optim.py:686-761) — float64, 25 Adam steps."""
+    from diffco_b200 import optim as OPT
+
+    g, robot, dc, start, target, init, opts = problem
+    options = {"n_waypoints": 12, "maxiter": 25, "history": True, "max_move_weight": 10, "collision_weight": 10,
+               "joint_limit_weight": 10, "safety_bias": 0.3, "max_speed": 0.6, "optimizer": torch.optim.Adam,
+               "optimizer_params": {"lr": 0.05}, "dense_check": False}
+    mask = torch.ones(12, dtype=torch.bool)
+    mask[[0, -1]] = False
+    ref = OPT.Weighted(robot, dc, dict(options)).step(init.clone(), mask=mask)
+    fused = OPT.Weighted(robot, dc, dict(options, fused=True)).step(init.clone(), mask=mask)
+    assert len(fused.misc["path_history"]) == len(ref.misc["path_history"])
+    assert (fused.x[[0, -1]] - init[[0, -1]]).abs().max() <= 1e-12  # end points are masked (wrap() may round them)
+    assert P.rel_to_max(fused.x, ref.x) <= 1e-9
+    for a, b in zip(fused.misc["path_history"], ref.misc["path_history"]):
+        assert P.rel_to_max(a, b) <= 1e-9
+    with pytest.raises(ValueError):
+        OPT.Weighted(robot, dc, dict(options, fused=True, dense_check=True)).step(init.clone())
+
+
+def test_weighted_step_graphed_cfg4_256_waypoints():
+    """BASELINE.json configs[3]: SE(2) base + 3-link arm, 3000 SVs, 256 waypoints, Adam — float32 model; the graphed
+    step against the autograd step (same arithmetic; float32 Adam amplifies rounding, hence the looser gate)."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+    from diffco_b200 import optim as OPT
+
+    dev = torch.device("cuda", 0)
+    robot, S, W = P.synthetic_model("se2arm", 3000, 1, seed=1234)
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine)
+    dc.support_points = S.float().to(dev)
+    dc.support_transformed = robot.fkine(dc.support_points)
+    dc.gains = W[:, 0].float().to(dev)
+    dc.rbf_nodes, dc.rbf_kernel = 0.05 * W[:, 0].float().to(dev), K.MultiQuadratic(1.0)
+    gen = torch.Generator().manual_seed(7)
+    a, b = P.sample_configs(robot, 2, gen).float()
+    init = a + (b - a) * torch.linspace(0, 1, 256)[:, None]
+    options = {"n_waypoints": 256, "maxiter": 40, "history": False, "max_move_weight": 10, "collision_weight": 10,
+               "joint_limit_weight": 10, "safety_bias": 0.0, "max_speed": 0.3, "optimizer": torch.optim.Adam,
+               "optimizer_params": {"lr": 0.02}, "dense_check": False}
+    mask = torch.ones(256, dtype=torch.bool)
+    mask[[0, -1]] = False
+    ref = OPT.Weighted(robot, dc, dict(options)).step(init.clone(), mask=mask)
+    fused = OPT.Weighted(robot, dc, dict(options, fused=True)).step(init.clone(), mask=mask)
+    err = P.rel_to_max(fused.x, ref.x)
+    print(f"cfg-4 256 waypoints x 40 Adam steps: graphed {fused.misc['time']*1e3:.1f} ms, autograd {ref.misc['time']*1e3:.1f} ms, "
+          f"max rel diff {err:.2e}")
+    assert err <= 2e-3

@@ -54,14 +54,16 @@ def test_struct_layouts_match_the_c_header(tmp_path):
     prog = tmp_path / "sizes.c"
     prog.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "diffco_b200.h"\n'
-        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(dc_dh_arm), sizeof(dc_fk_desc), sizeof(dc_kernel_desc),"
-        " sizeof(dc_supports), offsetof(dc_fk_desc, link_length), offsetof(dc_fk_desc, keypoints), offsetof(dc_fk_desc, arms),"
-        " offsetof(dc_dh_arm, base)); return 0;}\n")
+        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(dc_dh_arm), sizeof(dc_fk_desc),"
+        " sizeof(dc_kernel_desc), sizeof(dc_supports), offsetof(dc_fk_desc, link_length), offsetof(dc_fk_desc, keypoints),"
+        " offsetof(dc_fk_desc, arms), offsetof(dc_dh_arm, base), offsetof(dc_supports, tc_blob), sizeof(dc_traj_params),"
+        " offsetof(dc_traj_params, limits), offsetof(dc_traj_params, wrap)); return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(_lib.DhArm), C.sizeof(_lib.FkDesc), C.sizeof(_lib.KernelDesc), C.sizeof(_lib.Supports),
-            _lib.FkDesc.link_length.offset, _lib.FkDesc.keypoints.offset, _lib.FkDesc.arms.offset, _lib.DhArm.base.offset]
+            _lib.FkDesc.link_length.offset, _lib.FkDesc.keypoints.offset, _lib.FkDesc.arms.offset, _lib.DhArm.base.offset,
+            _lib.Supports.tc_blob.offset, C.sizeof(_lib.TrajParams), _lib.TrajParams.limits.offset, _lib.TrajParams.wrap.offset]
     assert got == want
 
 
