@@ -307,6 +307,12 @@ int dc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
   const int st = device_sm_count(&num_sms);
   if (st != DC_OK) return st;
   cudaStream_t cs = (cudaStream_t)stream;
+  if (grad_mode == DC_GRAD_JAC && sv->n_class == 1) {
+    // one class: the Jacobian [B,1,D] IS the summed gradient with a unit upstream gradient — lets the autograd path
+    // (functional._ScoreFunction asks for Jacobians) use the large-batch kernels, tensor cores included
+    grad_mode = DC_GRAD_SUM;
+    grad_out = nullptr;
+  }
 
   if (sv->dtype == DC_F64) {
     g_last_score_kernel = 0;
