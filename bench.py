@@ -293,6 +293,21 @@ def run_native(args):
     ms_dev, launches, clocks, _ = measure(step_dev)
     value = world * B * args.steps / (ms_dev * 1e-3)
 
+    # ---- the gathered result is right: the block another rank contributed equals a local evaluation of ITS shard ------
+    gather_check = None
+    if world > 1:
+        peer = (rank + 1) % world
+        _, _, q_peer = make_problem(peer, B)
+        s_all, g_all = scorer.score_and_grad(q_dev)
+        got = torch.cat([s_all, g_all], dim=1)[peer * B:(peer + 1) * B].clone()
+        s_loc, g_loc = scorer.local_score_and_grad(q_peer.float().to(dev))
+        want = torch.cat([s_loc, g_loc], dim=1)
+        bad = torch.tensor([0 if torch.equal(got, want) else 1], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        gather_check = "ok" if int(bad.item()) == 0 else "MISMATCH"
+        if gather_check != "ok":
+            raise SystemExit("bench.py: gathered records differ from a local evaluation of the peer's shard")
+
     # ---- dominant kernel alone (roofline): the fused score+grad launch without the collective ----------------
     def step_kernel():
         return scorer.local_score_and_grad(q_dev)
@@ -336,7 +351,11 @@ def run_native(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_sv": N_SV, "dof": DOF, "n_features": N_FEAT, "batch_per_gpu": B,
                        "global_batch": world * B, "kernel": "RQKernel(gamma=10,p=2)",
-                       "sharding": ("none" if world == 1 else f"batch rows over {world} ranks + 1 NCCL all-gather of [score|grad]"),
+                       "sharding": ("none" if world == 1 else
+                                    f"batch rows over {world} ranks; all-gather of [score|grad] " +
+                                    ("fused into the kernel epilogue (peer stores over NVLink + flag barrier)"
+                                     if getattr(scorer, "_peer", None) else "by one NCCL all_gather_into_tensor")),
+                       "gather_check": gather_check,
                        "l2": "flushed before every step (256 MiB memset, untimed); per-step CUDA events summed"},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,

@@ -84,6 +84,17 @@ class Supports(C.Structure):
     ]
 
 
+DC_MAX_PEERS = 8
+
+
+class PeerHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
+class PeerTable(C.Structure):
+    _fields_ = [("ptr", C.c_void_p * DC_MAX_PEERS)]
+
+
 class TrajParams(C.Structure):
     _fields_ = [
         ("dif_weight", C.c_double), ("max_move_weight", C.c_double), ("collision_weight", C.c_double),
@@ -122,6 +133,13 @@ PROTOTYPES = {
     "dc_perceptron_train": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
+    "dc_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(PeerHandle)]),
+    "dc_peer_open": (C.c_int, [C.POINTER(PeerHandle), C.POINTER(C.c_void_p)]),
+    "dc_peer_close": (C.c_int, [C.c_void_p]),
+    "dc_peer_free": (C.c_int, [C.c_void_p]),
+    "dc_peer_barrier": (C.c_int, [C.POINTER(PeerTable), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
+    "dc_score_grad_bcast": (C.c_int, [C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p, C.c_int64,
+                                      C.POINTER(PeerTable), C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "dc_traj_step": (C.c_int, [C.POINTER(FkDesc), C.POINTER(TrajParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dc_fk_vjp": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

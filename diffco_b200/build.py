@@ -27,7 +27,7 @@ TQ_VARIANTS = [("c1_score", 1, "M_SCORE"), ("c1_grad", 1, "M_GRAD"), ("c4_score"
 
 
 def _units():
-    units = [(n, os.path.join(CSRC, n + ".cu"), []) for n in ("dc_api", "dc_train", "dc_host", "dc_traj", "dc_score_tc", "dc_score_ls_f32", "dc_score_ls_f64")]
+    units = [(n, os.path.join(CSRC, n + ".cu"), []) for n in ("dc_api", "dc_train", "dc_host", "dc_traj", "dc_peer", "dc_score_tc", "dc_score_ls_f32", "dc_score_ls_f64")]
     for kname, kenum in TQ_KINDS.items():
         for vname, cw, mode in TQ_VARIANTS:
             sym = f"tq_{kname}_{vname}"

@@ -18,7 +18,7 @@ bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel
                               int grad_mode);
 int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q, int64_t batch,
                   void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out, int32_t grad_mode,
-                  int num_sms, cudaStream_t stream);
+                  int num_sms, cudaStream_t stream, const dc_peer_table* bcast = nullptr, int n_bcast = 0);
 
 #define DC_TQ_DECL(name) int name(int n_feat, ScoreArgs<float>& a, int num_sms, cudaStream_t stream);
 DC_TQ_DECL(tq_rq2_c1_score)

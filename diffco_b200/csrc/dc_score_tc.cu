@@ -66,8 +66,10 @@ bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel
 
 int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q, int64_t batch,
                   void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out, int32_t grad_mode,
-                  int num_sms, cudaStream_t stream) {
+                  int num_sms, cudaStream_t stream, const dc_peer_table* bcast, int n_bcast) {
   TcArgs a;
+  a.n_bcast = n_bcast;
+  for (int k = 0; k < DC_MAX_PEERS; ++k) a.bcast[k] = (bcast && k < n_bcast) ? static_cast<float*>(bcast->ptr[k]) : nullptr;
   a.fk = *fk;
   if (!make_radial_consts<float>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
   a.blob = static_cast<const unsigned char*>(sv->tc_blob);
@@ -112,6 +114,27 @@ int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_
   if (!tc_shape_ok(n_features, 1, DC_F32) || n >= (1 << 24)) return DC_ERR_UNSUPPORTED;
   return launch_pack_supports_tc(static_cast<const float*>(s_feat), static_cast<const float*>(w), n, n_features,
                                  static_cast<unsigned char*>(blob), (cudaStream_t)stream);
+}
+
+int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
+                        int64_t batch, const dc_peer_table* outs, int32_t n_outs, int64_t row_offset, int32_t grad_mode,
+                        dc_stream_t stream) {
+  if (!fk || !kernel || !sv || !outs || n_outs < 1 || n_outs > DC_MAX_PEERS || row_offset < 0) return DC_ERR_INVALID_ARG;
+  if (batch == 0) return DC_OK;
+  if (batch < 0 || !q || !sv->table) return DC_ERR_INVALID_ARG;
+  if (grad_mode != DC_GRAD_NONE && grad_mode != DC_GRAD_SUM) return DC_ERR_INVALID_ARG;
+  for (int k = 0; k < n_outs; ++k)
+    if (!outs->ptr[k] || (reinterpret_cast<uintptr_t>(outs->ptr[k]) & 15) != 0) return DC_ERR_INVALID_ARG;
+  if (!takes_tensor_core_kernel(*fk, *kernel, *sv, batch, grad_mode)) return DC_ERR_UNSUPPORTED;
+  int dev = 0, num_sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return DC_ERR_NO_DEVICE;
+  }
+  const int64_t rec = 1 + (grad_mode == DC_GRAD_SUM ? fk->dof : 0);
+  float* mine = static_cast<float*>(outs->ptr[0]) + row_offset * rec;  // the kernel adds (mine - outs[0]) to every base
+  return tc_score_grad(fk, kernel, sv, q, batch, mine, rec, grad_mode == DC_GRAD_SUM ? mine + 1 : nullptr, rec, nullptr,
+                       grad_mode, num_sms, (cudaStream_t)stream, outs, n_outs);
 }
 
 int dc_set_option(int32_t option, double value) { return tc_set_option(option, value); }

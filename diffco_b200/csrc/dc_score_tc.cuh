@@ -104,6 +104,8 @@ struct TcArgs {
   int f_pad;
   int n_tiles;
   int n_chunks;
+  float* bcast[DC_MAX_PEERS];  // n_bcast > 0: every fused record block is stored into each of these (row 0 = row 0 of the
+  int n_bcast;                 // gathered buffer; `score` then points at THIS rank's block of the first one)
   float err_coef;  // delta(rho) <= err_coef * (|x|^2 + max|s|^2)
   float tol_pair;  // admissible |w|-relative error of one pair
 };
@@ -789,12 +791,18 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
       asm volatile("bar.sync 1, 256;" ::: "memory");
       DC_TC_TRACE_TILE(7);
       if (fused) {
-        float* dst = a.score + (size_t)b_base * n_out;
+        // n_bcast > 0: the same block goes to every rank's gathered buffer (peer stores over NVLink) — the all-gather of
+        // the multi-GPU path, overlapped with the other tiles' arithmetic
+        const int n_dst = a.n_bcast > 0 ? a.n_bcast : 1;
+        const size_t off = (size_t)(a.score - (a.n_bcast > 0 ? a.bcast[0] : a.score)) + (size_t)b_base * n_out;
         const int n_words = nq * n_out;
-        if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-          for (int i = tid; i < n_words / 4; i += QT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
-        } else {
-          for (int i = tid; i < n_words; i += QT) dst[i] = os[i];
+        for (int k = 0; k < n_dst; ++k) {
+          float* dst = (a.n_bcast > 0 ? a.bcast[k] : a.score) + off;
+          if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            for (int i = tid; i < n_words / 4; i += QT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
+          } else {
+            for (int i = tid; i < n_words; i += QT) dst[i] = os[i];
+          }
         }
       } else {
         if (tid < nq) a.score[(size_t)(b_base + tid) * a.score_ld] = os[tid * n_out];

@@ -11,12 +11,14 @@ by world_size-2 gloo tests with a stub local scorer; the product path always com
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
-from . import functional
+from . import _lib, functional
 from ._lib import DC_GRAD_SUM
 
 
@@ -43,6 +45,93 @@ def all_gather_rows(buf: torch.Tensor, per: int, rank: int, group=None) -> None:
         dist.all_gather(views, mine.clone(), group=group)
 
 
+class _DevicePtr:
+    """Minimal __cuda_array_interface__ holder so torch can view memory owned by libdiffco_b200 (dc_peer_alloc)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerExchange:
+    """The gathered (G*b, C+D) record buffer of every rank of one box, mapped into every process (CUDA IPC over NVLink).
+
+    ``dc_score_grad_bcast`` stores each tile's records into all G buffers from the kernel's epilogue, so the all-gather
+    is fused into the scoring kernel; ``dc_peer_barrier`` (one flag round trip) then publishes the step.  Two buffers
+    alternate, so a rank that races ahead into step k+1 never overwrites records a slower rank still reads from step k
+    (it cannot reach step k+2 before everyone has passed the barrier of step k+1).
+    """
+
+    FLAG_BYTES = 256
+
+    def __init__(self, rows: int, width: int, dtype: torch.dtype, device: torch.device, group):
+        assert dtype == torch.float32
+        self.lib = _lib.load()
+        self.group, self.world, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.DC_MAX_PEERS:
+            raise RuntimeError(f"at most {_lib.DC_MAX_PEERS} ranks")
+        self.rows, self.width, self.device = rows, width, device
+        self.nbytes = self.FLAG_BYTES + 2 * rows * width * 4
+        self._own = C.c_void_p()
+        handle = _lib.PeerHandle()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.dc_peer_alloc(self.nbytes, C.byref(self._own), C.byref(handle)), "dc_peer_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.bytes), group=group)
+        self._opened = []
+        bases = []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                bases.append(self._own.value)
+                continue
+            h = _lib.PeerHandle()
+            C.memmove(h.bytes, hb, 64)
+            p = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(self.lib.dc_peer_open(C.byref(h), C.byref(p)), "dc_peer_open")
+            self._opened.append(p)
+            bases.append(p.value)
+        self.flags = _lib.PeerTable()
+        self.outs = [_lib.PeerTable(), _lib.PeerTable()]
+        for r, b in enumerate(bases):
+            self.flags.ptr[r] = b
+            for k in range(2):
+                self.outs[k].ptr[r] = b + self.FLAG_BYTES + k * rows * width * 4
+        self.views = [torch.as_tensor(_DevicePtr(self._own.value + self.FLAG_BYTES + k * rows * width * 4, (rows, width), "<f4"),
+                                      device=device) for k in range(2)]
+        self.epoch = 0
+        dist.barrier(group=group)  # every rank has mapped every buffer before anyone stores into them
+
+    def close(self):
+        for p in getattr(self, "_opened", []):
+            self.lib.dc_peer_close(p)
+        self._opened = []
+        if getattr(self, "_own", None) is not None and self._own.value:
+            self.lib.dc_peer_free(self._own)
+            self._own = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def score_and_grad(self, fk, kdesc, sv, q_shard: torch.Tensor) -> Optional[torch.Tensor]:
+        """Scores this rank's shard into every rank's buffer and publishes it.  Returns the (G*b, C+D) view holding the
+        global result, or None when the call is not one the tensor-core kernel takes (caller falls back to NCCL)."""
+        b = q_shard.shape[0]
+        k = self.epoch & 1
+        stream = functional._stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            st = self.lib.dc_score_grad_bcast(C.byref(fk), C.byref(kdesc), C.byref(sv.desc), q_shard.data_ptr(), b,
+                                              C.byref(self.outs[k]), self.world, self.rank * b, DC_GRAD_SUM, stream)
+            if st == -2:  # DC_ERR_UNSUPPORTED: same answer on every rank (it depends on shapes and options only)
+                return None
+            _lib.check(st, "dc_score_grad_bcast")
+            self.epoch += 1
+            _lib.check(self.lib.dc_peer_barrier(C.byref(self.flags), self.rank, self.world, self.epoch, stream), "dc_peer_barrier")
+        return self.views[k]
+
+
 class ShardedScorer:
     """score + gradient of a (replicated) perceptron over a batch sharded across the ranks of ``group``.
 
@@ -62,6 +151,8 @@ class ShardedScorer:
         self._buffers = {}
         self._pipe = None
         self._q_stage = None
+        self._peer = None          # PeerExchange for the current shard size (fused all-gather), or False: unavailable
+        self._peer_rows = None
         if local_fn is None:
             self._sv, self._kfun = checker._select(weights)
             self._fk = checker._fk_for(self._sv)
@@ -100,11 +191,44 @@ class ShardedScorer:
         """Every rank passes ITS shard (same row count b on every rank); returns the gathered global result
         (score (G*b, C), grad (G*b, D)) — rank r's rows are [r*b, (r+1)*b)."""
         b = q_shard.shape[0]
+        if self.world > 1 and self._local_fn is None and q_shard.is_cuda and self.dtype == torch.float32:
+            out = self._fused_all_gather(q_shard, b)
+            if out is not None:
+                return out[:, :self.n_class], out[:, self.n_class:]
         buf = self._buffer(self.world * b)
         self._local(q_shard, buf[self.rank * b:(self.rank + 1) * b])
         if self.world > 1:
             all_gather_rows(buf, b, self.rank, self.group)
         return buf[:, :self.n_class], buf[:, self.n_class:]
+
+    def _fused_all_gather(self, q_shard: torch.Tensor, b: int) -> Optional[torch.Tensor]:
+        """Tensor-core kernel with the all-gather fused into its epilogue (peer stores over NVLink + one flag barrier);
+        None when unavailable (DIFFCO_B200_PEER=0, IPC mapping failed, or the call is not a tensor-core one)."""
+        if self._peer is False or os.environ.get("DIFFCO_B200_PEER", "1") == "0":
+            return None
+        if self._peer is None or self._peer_rows != b:
+            if self._peer:
+                self._peer.close()
+            ok = torch.ones(1, dtype=torch.int32)
+            try:
+                self._peer = PeerExchange(self.world * b, self.record_width, self.dtype, self.device, self.group)
+                self._peer_rows = b
+            except Exception:
+                self._peer = False
+                ok.zero_()
+            # all ranks must take the same path: anyone's failure disables it everywhere
+            if dist.get_backend(self.group) == "nccl":
+                okd = ok.to(self.device)
+                dist.all_reduce(okd, op=dist.ReduceOp.MIN, group=self.group)
+                ok = okd.cpu()
+            else:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if self._peer:
+                    self._peer.close()
+                self._peer = False
+                return None
+        return self._peer.score_and_grad(self._fk, self._kfun.desc, self._sv, q_shard.detach().contiguous())
 
     def score_and_grad_global(self, q_global: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Every rank holds the same global batch (B, D); rank r evaluates rows shard_bounds(B, G, r) and the result for

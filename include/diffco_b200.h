@@ -209,6 +209,27 @@ int dc_perceptron_train(const dc_kernel_desc* kernel, const void* x_feat, const 
                         void* kernel_matrix, void* diag, int32_t legacy_multi, int64_t* iterations_out, dc_stream_t stream);
 
 /*
+ * Multi-GPU (one process per GPU of one box).  dc_peer_alloc gives a zeroed device buffer plus a handle
+ * other processes open with dc_peer_open (CUDA IPC over NVLink).  dc_score_grad_bcast is dc_score_grad with the fused
+ * [score | grad] record of row b stored at row (row_offset + b) of EVERY buffer in `outs` (this rank's own and its peers'
+ * mappings) — the all-gather happens inside the kernel's epilogue.  Returns DC_ERR_UNSUPPORTED when the call does not go
+ * to the tensor-core kernel (use dc_score_grad + a collective then).  dc_peer_barrier (same stream, afterwards) publishes
+ * the stores: flags->ptr[r] is rank r's flag array (>= world uint32, zero-initialised, e.g. the head of a dc_peer_alloc
+ * buffer) as mapped in this process; `epoch` must increase by one per call.
+ */
+#define DC_MAX_PEERS 8
+typedef struct dc_peer_handle { unsigned char bytes[64]; } dc_peer_handle;
+typedef struct dc_peer_table { void* ptr[DC_MAX_PEERS]; } dc_peer_table;
+int dc_peer_alloc(int64_t bytes, void** ptr, dc_peer_handle* handle);
+int dc_peer_open(const dc_peer_handle* handle, void** ptr);
+int dc_peer_close(void* ptr);
+int dc_peer_free(void* ptr);
+int dc_peer_barrier(const dc_peer_table* flags, int32_t rank, int32_t world, uint32_t epoch, dc_stream_t stream);
+int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
+                        int64_t batch, const dc_peer_table* outs, int32_t n_outs, int64_t row_offset, int32_t grad_mode,
+                        dc_stream_t stream);
+
+/*
  * One iteration of the reference's penalty trajectory optimiser (Weighted.step, diffco/optim.py:706-752; the same terms
  * as adam_traj_optimize, optim.py:86-127) for W waypoints in one launch: control points, path length, max-move and
  * joint-limit hinges, the collision hinge on `score` (+ `score_grad` = d score/dp from dc_score_grad; both NULL = no
