@@ -266,6 +266,9 @@ def run_native(args):
         t0 = time.perf_counter()
         for a, b in evs:
             flush.zero_()  # evict the previous step's inputs/outputs from the 126 MB L2 (untimed)
+            if world > 1:
+                scorer.align()  # untimed: the flushes end at different moments on different GPUs; without this the wait
+                                # for the slowest flush would be charged to the step through the step's own collective
             a.record(stream)
             step_fn()
             b.record(stream)
@@ -356,7 +359,9 @@ def run_native(args):
                                     ("fused into the kernel epilogue (peer stores over NVLink + flag barrier)"
                                      if getattr(scorer, "_peer", None) else "by one NCCL all_gather_into_tensor")),
                        "gather_check": gather_check,
-                       "l2": "flushed before every step (256 MiB memset, untimed); per-step CUDA events summed"},
+                       "l2": "flushed before every step (256 MiB memset, untimed" +
+                             ("; ranks re-aligned by an untimed device barrier after it" if world > 1 else "") +
+                             "); per-step CUDA events summed"},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": kernel_name, "kernel_ms": per_launch_s * 1e3,

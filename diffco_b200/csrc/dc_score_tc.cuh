@@ -796,12 +796,26 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         const int n_dst = a.n_bcast > 0 ? a.n_bcast : 1;
         const size_t off = (size_t)(a.score - (a.n_bcast > 0 ? a.bcast[0] : a.score)) + (size_t)b_base * n_out;
         const int n_words = nq * n_out;
-        for (int k = 0; k < n_dst; ++k) {
-          float* dst = (a.n_bcast > 0 ? a.bcast[k] : a.score) + off;
-          if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            for (int i = tid; i < n_words / 4; i += QT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
-          } else {
-            for (int i = tid; i < n_words; i += QT) dst[i] = os[i];
+        if (a.n_bcast > 0 && (n_words & 3) == 0) {
+          // one bulk TMA store of the whole block per destination (shared -> peer global, large NVLink packets, no
+          // thread is held by the transfer); the block is released below once the copies have read it
+          if (tid == 0) {
+            fence_proxy_async();
+            for (int k = 0; k < n_dst; ++k)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.bcast[k] + off),
+                           "r"(smem_u32(os)), "r"(n_words * 4)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+        } else {
+          for (int k = 0; k < n_dst; ++k) {
+            float* dst = (a.n_bcast > 0 ? a.bcast[k] : a.score) + off;
+            if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+              for (int i = tid; i < n_words / 4; i += QT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
+            } else {
+              for (int i = tid; i < n_words; i += QT) dst[i] = os[i];
+            }
           }
         }
       } else {
@@ -818,6 +832,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
     }
   }
 
+  if (tid == 0 && a.n_bcast > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // peer stores performed
   tc_fence_before();
   __syncthreads();
   if (warp == L::CTRL_WARP) {

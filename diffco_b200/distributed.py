@@ -98,7 +98,8 @@ class PeerExchange:
                 self.outs[k].ptr[r] = b + self.FLAG_BYTES + k * rows * width * 4
         self.views = [torch.as_tensor(_DevicePtr(self._own.value + self.FLAG_BYTES + k * rows * width * 4, (rows, width), "<f4"),
                                       device=device) for k in range(2)]
-        self.epoch = 0
+        self.epoch = 0   # barriers so far
+        self.steps = 0   # scoring steps so far (selects the buffer)
         dist.barrier(group=group)  # every rank has mapped every buffer before anyone stores into them
 
     def close(self):
@@ -119,7 +120,7 @@ class PeerExchange:
         """Scores this rank's shard into every rank's buffer and publishes it.  Returns the (G*b, C+D) view holding the
         global result, or None when the call is not one the tensor-core kernel takes (caller falls back to NCCL)."""
         b = q_shard.shape[0]
-        k = self.epoch & 1
+        k = self.steps & 1
         stream = functional._stream_ptr(self.device)
         with torch.cuda.device(self.device):
             st = self.lib.dc_score_grad_bcast(C.byref(fk), C.byref(kdesc), C.byref(sv.desc), q_shard.data_ptr(), b,
@@ -127,9 +128,16 @@ class PeerExchange:
             if st == -2:  # DC_ERR_UNSUPPORTED: same answer on every rank (it depends on shapes and options only)
                 return None
             _lib.check(st, "dc_score_grad_bcast")
-            self.epoch += 1
-            _lib.check(self.lib.dc_peer_barrier(C.byref(self.flags), self.rank, self.world, self.epoch, stream), "dc_peer_barrier")
+        self.steps += 1
+        self.barrier()
         return self.views[k]
+
+    def barrier(self):
+        """Device-side barrier of all ranks on the current stream (one flag round trip, no host involvement)."""
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dc_peer_barrier(C.byref(self.flags), self.rank, self.world, self.epoch,
+                                                functional._stream_ptr(self.device)), "dc_peer_barrier")
 
 
 class ShardedScorer:
@@ -200,6 +208,16 @@ class ShardedScorer:
         if self.world > 1:
             all_gather_rows(buf, b, self.rank, self.group)
         return buf[:, :self.n_class], buf[:, self.n_class:]
+
+    def align(self) -> None:
+        """Stream-ordered rendezvous of all ranks (benchmarks: line the ranks up after untimed work)."""
+        if self.world == 1:
+            return
+        if self._peer:
+            self._peer.barrier()
+        else:
+            t = torch.zeros(1, device=self.device)
+            dist.all_reduce(t, group=self.group)
 
     def _fused_all_gather(self, q_shard: torch.Tensor, b: int) -> Optional[torch.Tensor]:
         """Tensor-core kernel with the all-gather fused into its epilogue (peer stores over NVLink + one flag barrier);
