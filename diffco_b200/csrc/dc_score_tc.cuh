@@ -209,7 +209,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 60000000000LL) __trap();  // ~30 s: a protocol bug, not a slow launch
   }
 }
 

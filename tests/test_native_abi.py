@@ -84,6 +84,45 @@ def test_layout_helper_and_validation_without_a_device(lib):
     assert lib.dc_launch_count() >= 0
 
 
+def test_tensor_core_peer_and_trajectory_entry_points_validate_arguments(lib):
+    """Argument checks of the entry points added with ABI version 2 — all of them return before touching a device."""
+    from diffco_b200 import _lib
+
+    n = C.c_int64()
+    assert lib.dc_supports_tc_bytes(2000, 14, 1, _lib.DC_F32, C.byref(n)) == 0
+    assert n.value == 21 * 21888 + 32  # 21 chunks of 96 supports + the scale trailer
+    assert lib.dc_supports_tc_bytes(2000, 15, 1, _lib.DC_F32, C.byref(n)) == -2   # F > 14
+    assert lib.dc_supports_tc_bytes(2000, 14, 4, _lib.DC_F32, C.byref(n)) == -2   # multi-class
+    assert lib.dc_supports_tc_bytes(2000, 14, 1, _lib.DC_F64, C.byref(n)) == -2   # float64
+    assert lib.dc_supports_tc_bytes(0, 14, 1, _lib.DC_F32, C.byref(n)) == -1
+    assert lib.dc_pack_supports_tc(None, None, 10, 14, None, None) == -1
+    assert lib.dc_pack_supports_tc(64, 64, 10, 14, 72, None) == -1                # blob not 128-byte aligned
+    saved = [lib.dc_get_option(k) for k in (1, 2, 3, 4)]
+    try:
+        assert lib.dc_set_option(_lib.DC_OPT_TC_ERR_COEF, 1e-6) == 0 and lib.dc_get_option(_lib.DC_OPT_TC_ERR_COEF) == 1e-6
+        assert lib.dc_set_option(_lib.DC_OPT_TC_ENABLE, 0.0) == 0 and lib.dc_get_option(_lib.DC_OPT_TC_ENABLE) == 0.0
+        assert lib.dc_set_option(_lib.DC_OPT_TC_TOL_PAIR, 0.0) == -1 and lib.dc_set_option(_lib.DC_OPT_TC_MIN_BATCH, 0.5) == -1
+        assert lib.dc_set_option(77, 1.0) == -1
+    finally:
+        for k, v in zip((1, 2, 3, 4), saved):
+            assert lib.dc_set_option(k, v) == 0
+    assert lib.dc_last_score_kernel() in (-1, 0, 1, 2)
+    tab = _lib.PeerTable()
+    assert lib.dc_peer_barrier(C.byref(tab), 0, 2, 1, None) == -1       # unmapped flag arrays
+    assert lib.dc_peer_barrier(C.byref(tab), 3, 2, 1, None) == -1 and lib.dc_peer_barrier(None, 0, 1, 1, None) == -1
+    assert lib.dc_peer_alloc(0, None, None) == -1 and lib.dc_peer_open(None, None) == -1
+    assert lib.dc_peer_close(None) == 0 and lib.dc_peer_free(None) == 0
+    fk, kd, sv = _lib.FkDesc(), _lib.KernelDesc(_lib.DC_K_RQ, 2, 10.0), _lib.Supports()
+    assert lib.dc_score_grad_bcast(C.byref(fk), C.byref(kd), C.byref(sv), 64, 8, C.byref(tab), 0, 0, 1, None) == -1
+    assert lib.dc_score_grad_bcast(C.byref(fk), C.byref(kd), C.byref(sv), 64, 8, C.byref(tab), 2, 0, 1, None) == -1  # null outs
+    prm = _lib.TrajParams()
+    assert lib.dc_traj_step(None, C.byref(prm), 8, 0, None, None, None, None, None, None, None, None, None) == -1
+    fk.type, fk.dof, fk.n_points, fk.point_dim, fk.n_links = _lib.DC_FK_PLANAR_CHAIN, 3, 3, 2, 3
+    assert lib.dc_traj_step(C.byref(fk), C.byref(prm), 1, 0, 64, None, None, None, 64, 64, 64, 64, None) == -1   # < 2 waypoints
+    assert lib.dc_traj_step(C.byref(fk), C.byref(prm), 8, 0, 64, 64, None, None, 64, 64, 64, 64, None) == -1    # score without grad
+    assert lib.dc_traj_step(C.byref(fk), C.byref(prm), 8, 0, 64, None, None, None, 64, 64, 64, 64, None) == -1  # lr == 0
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_product_path_fails_loudly_without_cuda():
     """No CPU fallback: scoring without a CUDA device raises instead of silently computing elsewhere."""
