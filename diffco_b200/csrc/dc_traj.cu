@@ -46,7 +46,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 1) traj_step_kernel(const __grid_constant__ TrajArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* cps = reinterpret_cast<T*>(smem_raw);                  // [W][F]
-  T* red = cps + (size_t)a.n_wp * a.n_feat;                 // [4][8] per-warp partial sums
+  T* red = cps + (size_t)a.n_wp * a.n_feat;                 // [5][8] per-warp partial sums
   const int tid = threadIdx.x, W = a.n_wp, F = a.n_feat, D = a.fk.dof;
   const int M = a.fk.type == DC_FK_NONE ? F : a.fk.n_points, dim = a.fk.type == DC_FK_NONE ? 1 : a.fk.point_dim;
   const dc_traj_params& P = a.prm;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256, 1) traj_step_kernel(const __grid_constant
   const T v2 = (T)(P.max_speed * P.max_speed);
   const T bc1 = (T)(1.0 - pow(P.beta1, step_d)), bc2_sqrt = (T)sqrt(1.0 - pow(P.beta2, step_d));
   const T step_size = (T)P.lr / bc1;
-  T acc_len = 0, acc_col = 0, acc_jl = 0, acc_mm = 0;
+  T acc_len = 0, acc_col = 0, acc_jl = 0, acc_mm = 0, acc_g2 = 0;
   for (int w = tid; w < W; w += blockDim.x) {
     T q[DC_MAX_DOF], gq[DC_MAX_DOF], gcp[DC_MAX_FEATURES];
 #pragma unroll
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256, 1) traj_step_kernel(const __grid_constant
         g += (T)P.joint_limit_weight * ((q[i] > hi ? (T)1 : (T)0) - (q[i] < lo ? (T)1 : (T)0));
       }
       if (a.mask != nullptr) g *= a.mask[idx];
+      acc_g2 = fma(g, g, acc_g2);
       // torch.optim.Adam (no weight decay / amsgrad): lerp, addcmul, addcdiv
       T m1 = a.exp_avg[idx], m2 = a.exp_avg_sq[idx];
       m1 = m1 + (g - m1) * (T)(1.0 - P.beta1);
@@ -127,9 +128,9 @@ __global__ void __launch_bounds__(256, 1) traj_step_kernel(const __grid_constant
     }
   }
   // fixed-order block reduction of the four sums
-  T vals[4] = {acc_len, acc_col, acc_jl, acc_mm};
+  T vals[5] = {acc_len, acc_col, acc_jl, acc_mm, acc_g2};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 5; ++k) {
     T v = vals[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(256, 1) traj_step_kernel(const __grid_constant
   }
   __syncthreads();
   if (tid == 0) {
-    T s[4];
-    for (int k = 0; k < 4; ++k) {
+    T s[5];
+    for (int k = 0; k < 5; ++k) {
       s[k] = 0;
       for (int wp = 0; wp < (int)(blockDim.x >> 5); ++wp) s[k] += red[k * 8 + wp];
     }
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(256, 1) traj_step_kernel(const __grid_constant
     a.terms[2] = s[2];
     a.terms[3] = s[3];
     a.terms[4] = (T)P.collision_weight * s[1] + (T)P.max_move_weight * s[3] + (T)P.joint_limit_weight * s[2];
+    a.terms[5] = s[4];  // |masked gradient|^2 (adam_traj_optimize's stopping test, optim.py:121-122)
     *a.step = step_d;
   }
 }
@@ -168,7 +170,7 @@ static int launch_traj_step(const dc_fk_desc* fk, const dc_traj_params* prm, int
   a.terms = static_cast<T*>(terms);
   a.n_wp = (int)n_wp;
   a.n_feat = fk->type == DC_FK_NONE ? fk->dof : fk->n_points * fk->point_dim;
-  const size_t smem = sizeof(T) * ((size_t)n_wp * a.n_feat + 32);
+  const size_t smem = sizeof(T) * ((size_t)n_wp * a.n_feat + 40);
   if (smem > 200 * 1024) return DC_ERR_UNSUPPORTED;
   auto kern = traj_step_kernel<T>;
   static bool attr_set = false;

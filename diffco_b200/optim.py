@@ -7,10 +7,10 @@ import.  ``dist_est`` is any callable with the protocol of SURVEY.md §8b — no
 Jacobian behind autograd.  The optimisation drivers themselves are host logic (Adam / scipy SLSQP over ~20 waypoints);
 what they spend their time in — dist_est and robot.fkine with gradients — runs on the GPU.
 
-``Weighted.step`` additionally has a device-resident fast path (``options['fused'] = True``, diffco_b200/trajopt.py): the
-penalty (collision hinge + max-move + joint-limit + path length) and its gradient are assembled analytically from
-``dc_score_grad`` / ``dc_fk_forward`` / ``dc_fk_vjp`` launches plus a dozen element-wise ops, and the whole step including
-the Adam update is ONE CUDA graph replayed per iteration.
+``Weighted.step`` and ``adam_traj_optimize`` additionally have a device-resident fast path (``options['fused'] = True``,
+diffco_b200/trajopt.py): the penalty (collision hinge + max-move + joint-limit + path length), its analytic gradient,
+the Adam update and ``robot.wrap`` are ONE launch (``dc_traj_step``) after ``dc_score_grad``, both captured in a CUDA graph
+that is replayed per iteration.
 
 Not provided: ``trustconstr_traj_optimize`` (needs second derivatives of dist_est; optim.py:380-391) and
 ``gradient_free_traj_optimize`` — both raise NotImplementedError rather than silently doing something else.
@@ -86,10 +86,50 @@ def adam_traj_optimize(robot, dist_est, start_cfg, target_cfg, options):
     valid = {"obj": np.inf, "p": None, "step": None, "trial": None}
     histories, cnt_check, found = [], 0, False
     t0 = time.time()
+    stepper = None
+    if options.get("fused", False):
+        # device-resident fast path (diffco_b200/trajopt.py): every iteration is one CUDA-graph replay of
+        # dc_score_grad + dc_traj_step; the bookkeeping below is the reference's, fed from the kernel's six terms
+        from . import trajopt
+
+        target = trajopt.scorer_of(dist_est)
+        if target is None or isinstance(safety_margin, torch.Tensor):
+            raise ValueError("options['fused'] = True needs dist_est = <diffco_b200 perceptron>.score / .poly_score / .rbf_score "
+                             "and a scalar safety_margin")
     for trial in range(n_trials):
         path, trivial = _initial_path(robot, start_cfg, target_cfg, n_waypoints, trial, options)
         if trivial:
             return _trivial_record(robot, path, start_cfg, target_cfg, seed, t0)
+        if options.get("fused", False):
+            checker, weights = target
+            if stepper is None:
+                mask = torch.ones(len(path), dtype=torch.bool)
+                mask[[0, -1]] = False  # the end points are fixed
+                stepper = trajopt.GraphedPenaltyStep(robot, checker, weights, path.to(checker.device), mask,
+                                                     dif_weight=_DIF_WEIGHT, max_move_weight=_MAX_MOVE_WEIGHT,
+                                                     collision_weight=_COLLISION_WEIGHT, joint_limit_weight=_JOINT_LIMIT_WEIGHT,
+                                                     safety_bias=-float(safety_margin), max_speed=max_speed, lr=lr, wrap=False)
+            else:
+                stepper.reset(path)
+            history = []
+            for step in range(maxiter):
+                t = stepper.replay()  # [path length, collision, joint limit, max move, constraint, |grad|^2] before the update
+                cnt_check += len(path)
+                if keep_history:
+                    history.append(stepper.p.detach().clone())
+                ov, cv = _DIF_WEIGHT * t[0], t[4]
+                lv = ov + cv
+                if lv < lowest["loss"]:
+                    lowest.update(loss=lv, obj=ov, p=stepper.p.detach().clone(), step=step, trial=trial)
+                if cv <= 1e-2 and ov < valid["obj"]:
+                    valid.update(obj=ov, p=stepper.p.detach().clone(), step=step, trial=trial)
+                if cv <= 1e-2 and t[5] ** 0.5 < 1e-4:
+                    break
+            histories.append(history)
+            if valid["p"] is not None:
+                found = True
+                break
+            continue
         p = path.requires_grad_(True)
         opt = torch.optim.Adam([p], lr=lr)
         history = []

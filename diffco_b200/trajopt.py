@@ -44,19 +44,20 @@ def _eligible(opt, p):
     return None
 
 
-class GraphedWeightedStep:
-    """One ``Weighted.step`` iteration — a ``dc_score_grad`` launch and a ``dc_traj_step`` launch — as a replayable CUDA
-    graph over static buffers."""
+class GraphedPenaltyStep:
+    """One iteration of the reference's penalty optimisers — a ``dc_score_grad`` launch and a ``dc_traj_step`` launch — as
+    a replayable CUDA graph over static buffers.  ``terms`` (device, 6 values) holds, for the waypoints BEFORE the update
+    of the last replay: path length, collision, joint limit, max move, constraint loss, |masked gradient|^2."""
 
-    def __init__(self, opt, p, mask=None):
-        why = _eligible(opt, p)
-        if why is not None:
-            raise ValueError(f"options['fused'] = True: {why}")
-        self.o = opt
+    def __init__(self, robot, checker, weights, p, mask=None, *, dif_weight=1.0, max_move_weight=10.0, collision_weight=10.0,
+                 joint_limit_weight=10.0, safety_bias=0.0, max_speed=1.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, wrap=True):
         self.lib = _lib.load()
-        self.sv, self.kfun = opt.checker._select("rbf")
-        self.fk_score = opt.checker._fk_for(self.sv)
-        self.fk_path = opt.robot.fk_desc
+        self.sv, self.kfun = checker._select(weights)
+        if self.sv.n_class != 1:
+            raise ValueError("the graphed step needs a single-class checker")
+        self.fk_score = checker._fk_for(self.sv)
+        self.fk_path = robot.fk_desc
+        self.collision_weight = float(collision_weight)
         self.W, self.D = p.shape
         dev, dt = p.device, p.dtype
         self.dtype_code = functional._dtype_code(dt)
@@ -66,22 +67,19 @@ class GraphedWeightedStep:
             m = torch.as_tensor(mask, device=dev)
             m = m.reshape(-1, 1) if m.ndim == 1 else m
             self.mask = m.to(dt).expand(self.W, self.D).contiguous()
-        self.terms = torch.zeros(5, device=dev, dtype=dt)  # path length, collision, joint limit, max move, constraint
+        self.terms = torch.zeros(6, device=dev, dtype=dt)
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.p), torch.zeros_like(self.p)
         self.step_count = torch.zeros((), device=dev, dtype=torch.float64)
-        hp = opt.optimizer_params
-        b1, b2 = hp.get("betas", (0.9, 0.999))
         prm = TrajParams()
-        prm.dif_weight, prm.max_move_weight = float(opt.dif_weight), float(opt.max_move_weight)
-        prm.collision_weight, prm.joint_limit_weight = float(opt.collision_weight), float(opt.joint_limit_weight)
-        prm.safety_bias, prm.max_speed = float(opt.safety_bias), float(opt.max_speed)
-        prm.lr, prm.beta1, prm.beta2, prm.eps = float(hp.get("lr", 1e-3)), float(b1), float(b2), float(hp.get("eps", 1e-8))
-        lim = opt.robot.limits.to(dtype=dt).double().cpu()  # the reference compares against limits in the path's dtype
-        probe = torch.full((1, self.D), 100.0)
-        wrapped = opt.robot.wrap(probe)[0] != 100.0            # which coordinates robot.wrap maps to [-pi, pi)
+        prm.dif_weight, prm.max_move_weight = float(dif_weight), float(max_move_weight)
+        prm.collision_weight, prm.joint_limit_weight = float(collision_weight), float(joint_limit_weight)
+        prm.safety_bias, prm.max_speed = float(safety_bias), float(max_speed)
+        prm.lr, prm.beta1, prm.beta2, prm.eps = float(lr), float(betas[0]), float(betas[1]), float(eps)
+        lim = robot.limits.to(dtype=dt).double().cpu()  # the reference compares against limits in the path's dtype
+        wrapped = robot.wrap(torch.full((1, self.D), 100.0))[0] != 100.0 if wrap else torch.zeros(self.D, dtype=torch.bool)
         for i in range(self.D):
             prm.limits[i][0], prm.limits[i][1] = float(lim[i, 0]), float(lim[i, 1])
-            prm.wrap[i] = int(wrapped[i])
+            prm.wrap[i] = int(wrapped[i])  # which coordinates robot.wrap maps to [-pi, pi)
         self.prm = prm
         # warm-up outside the capture (lazily initialised kernel attributes), then rewind
         p0 = self.p.clone()
@@ -91,20 +89,29 @@ class GraphedWeightedStep:
             for _ in range(2):
                 self._one_step()
         torch.cuda.current_stream(dev).wait_stream(side)
-        with torch.no_grad():
-            self.p.copy_(p0)
-            self.exp_avg.zero_()
-            self.exp_avg_sq.zero_()
-            self.step_count.zero_()
+        self.reset(p0)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._one_step()
 
     @torch.no_grad()
+    def reset(self, p_new):
+        """New waypoints (same shape), fresh optimiser state; the captured graph is reused."""
+        self.p.copy_(p_new.to(device=self.p.device, dtype=self.p.dtype))
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_count.zero_()
+
+    def replay(self):
+        """Runs one iteration and returns the six terms as Python floats (the one host round trip per step)."""
+        self.graph.replay()
+        return self.terms.tolist()
+
+    @torch.no_grad()
     def _one_step(self):
-        o, p = self.o, self.p
+        p = self.p
         s_ptr = g_ptr = None
-        if o.collision_weight != 0:
+        if self.collision_weight != 0:
             # optim.py:711-713: dist_est casts the waypoints to the model dtype (kernel_perceptrons.py:313)
             s, g = functional.score_grad(self.fk_score, self.kfun.desc, self.sv, p.to(self.sv.dtype), DC_GRAD_SUM)
             self._s, self._g = s.to(p.dtype).contiguous(), g.to(p.dtype).contiguous()
@@ -116,18 +123,31 @@ class GraphedWeightedStep:
                                        functional._stream_ptr(p.device))
         _lib.check(st, "dc_traj_step")
 
+
+class GraphedWeightedStep(GraphedPenaltyStep):
+    """``Weighted.step`` (optim.py:686-761) on the graphed iteration."""
+
+    def __init__(self, opt, p, mask=None):
+        why = _eligible(opt, p)
+        if why is not None:
+            raise ValueError(f"options['fused'] = True: {why}")
+        self.o = opt
+        hp = opt.optimizer_params
+        super().__init__(opt.robot, opt.checker, "rbf", p, mask, dif_weight=opt.dif_weight, max_move_weight=opt.max_move_weight,
+                         collision_weight=opt.collision_weight, joint_limit_weight=opt.joint_limit_weight,
+                         safety_bias=opt.safety_bias, max_speed=opt.max_speed, lr=hp.get("lr", 1e-3),
+                         betas=hp.get("betas", (0.9, 0.999)), eps=hp.get("eps", 1e-8), wrap=True)
+
     def run(self, maxiter, verbose=False):
         o, history = self.o, []
         for step in range(maxiter):
-            self.graph.replay()
-            t = self.terms.tolist()  # the one host round trip per step: the reference's early-exit test
-            c = t[4]
+            t = self.replay()
             if verbose and o._logger is not None and (step % max(1, maxiter // 5) == 0 or step + 1 == maxiter):
                 o._logger.info(f"obj {t[0]:.3f}x1, col {t[1]:.3f}x{o.collision_weight}, jnt {t[2]:.3f}x{o.joint_limit_weight}, "
                                f"spd {t[3]:.3f}x{o.max_move_weight}.")
             if o.history:
                 history.append(o.normalizer(self.p.detach().cpu()))
-            if c <= 0.5:
+            if t[4] <= 0.5:  # optim.py:747-752
                 break
         return self.p.detach(), history
 
@@ -135,3 +155,16 @@ class GraphedWeightedStep:
 def fused_weighted_steps(opt, p, maxiter, mask=None, verbose=False):
     """Entry point used by ``Weighted.step`` when ``options['fused']`` is set."""
     return GraphedWeightedStep(opt, p, mask).run(maxiter, verbose)
+
+
+def scorer_of(dist_est):
+    """(perceptron, 'gains' | 'rbf') when ``dist_est`` is a bound scoring method of a diffco_b200 perceptron — what
+    ``adam_traj_optimize(..., options['fused'] = True)`` needs to put the collision term on the graphed step."""
+    owner, name = getattr(dist_est, "__self__", None), getattr(dist_est, "__name__", "")
+    if owner is None or not hasattr(owner, "_select") or not hasattr(owner, "_fk_for"):
+        return None
+    if name in ("score", "score_original"):
+        return owner, "gains"
+    if name in ("poly_score", "rbf_score"):
+        return owner, "rbf"
+    return None

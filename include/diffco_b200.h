@@ -235,7 +235,8 @@ int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, cons
  * joint-limit hinges, the collision hinge on `score` (+ `score_grad` = d score/dp from dc_score_grad; both NULL = no
  * collision term), the analytic gradient of the weighted sum, the `mask` multipliers, torch.optim.Adam's update and
  * robot.wrap.  p[W,dof], exp_avg, exp_avg_sq are IN/OUT device arrays of `dtype`; `step` is the optimiser's step count
- * (device double, incremented); terms[5] receives {path length, collision, joint limit, max move, constraint loss}.
+ * (device double, incremented); terms[6] receives {path length, collision, joint limit, max move, constraint loss,
+ * squared norm of the masked gradient}.
  */
 typedef struct dc_traj_params {
   double dif_weight, max_move_weight, collision_weight, joint_limit_weight; /* optim.py:19-22,669-676 */

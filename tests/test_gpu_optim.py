@@ -136,3 +136,19 @@ def test_weighted_step_graphed_cfg4_256_waypoints():
     print(f"cfg-4 256 waypoints x 40 Adam steps: graphed {fused.misc['time']*1e3:.1f} ms, autograd {ref.misc['time']*1e3:.1f} ms, "
           f"max rel diff {err:.2e}")
     assert err <= 2e-3
+
+
+def test_adam_traj_optimize_graphed_matches_autograd_and_reference(problem):
+    """adam_traj_optimize(options['fused'] = True): the reference's bookkeeping (optim.py:86-163) on the CUDA-graph-replayed
+    step; same record as the autograd run (float64) and the reference's golden record within its 1e-4 gate."""
+    from diffco_b200 import optim as OPT
+
+    g, robot, dc, start, target, init, opts = problem
+    base = OPT.adam_traj_optimize(robot, dc.poly_score, start, target, dict(opts, init_solution=init.clone()))
+    rec = OPT.adam_traj_optimize(robot, dc.poly_score, start, target, dict(opts, init_solution=init.clone(), fused=True))
+    assert rec["success"] == base["success"] and rec["cnt_check"] == base["cnt_check"]
+    assert np.abs(np.array(rec["solution"]) - np.array(base["solution"])).max() <= 1e-9
+    assert abs(rec["cost"] - base["cost"]) <= 1e-9 * max(1.0, abs(base["cost"]))
+    assert np.abs(np.array(rec["solution"]) - g["adam_solution"]).max() <= 1e-4
+    with pytest.raises(ValueError):
+        OPT.adam_traj_optimize(robot, lambda q: dc.poly_score(q), start, target, dict(opts, init_solution=init.clone(), fused=True))
