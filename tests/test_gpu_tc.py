@@ -190,3 +190,22 @@ def test_dispatch_rules(dev, lib):
     assert cuda_support_set(robot2, S2, W2, torch.float32, dev).tc_blob is None
     robot3, S3, W3 = P.synthetic_model("panda", 200, 1, seed=343)
     assert cuda_support_set(robot3, S3, W3, torch.float32, dev).tc_blob is None
+
+
+@pytest.mark.parametrize("n_sv", [50, 96, 97, 193])
+def test_support_counts_around_the_chunk_size(n_sv, dev, lib):
+    """Half a chunk, exactly one chunk, one chunk + 1, two chunks + 1 (chunk = 96 supports; padding rows must vanish).
+    (A single support is left to the dispatcher: with no pair inside the kernel's width the batch maximum is a far-field
+    value, and the tensor-core path's bound — tol_pair of the WEIGHT per pair — is then ~1e-5 of that maximum.)"""
+    from diffco_b200 import _lib
+
+    robot, S, W = P.synthetic_model("planar7", n_sv, 1, seed=350 + n_sv)
+    q = P.sample_configs(robot, 4200, torch.Generator().manual_seed(351)).float().double()
+    q[17] = S[0]
+    kfun, kspec = kernel_pair("rq")
+    s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q)
+    sv = cuda_support_set(robot, S, W, torch.float32, dev)
+    sv.desc.tc_s2max = 0.0  # "unknown": the dispatcher's width heuristic (few supports -> small max|s|^2) stays out of the way
+    s, g, which = run(lib, robot, kfun, sv, q.to(device=dev, dtype=torch.float32), _lib.DC_GRAD_SUM, tc=True)
+    assert which == TC
+    assert rel(s, s_ref) <= 1e-5 and rel(g, g_ref) <= 1e-5
