@@ -433,3 +433,41 @@ def dense_path(q, max_step=2.0, max_step_num=None):
         out.append(q[i] + ir * delta * max_step / dist)
     out.append(q[-1:])
     return torch.cat(out)
+
+
+# --------------------------------------------------------------------------------------------------
+# Weighted.step (optim.py:686-761): the penalty optimiser's loop, restated
+# --------------------------------------------------------------------------------------------------
+
+
+def weighted_step(p0, fk, score_fn, limits, wrap_fn, *, maxiter, collision_weight, max_move_weight, joint_limit_weight,
+                  safety_bias, max_speed, lr, dense_check, mask=None, dif_weight=1.0):
+    """optim.py:706-752.  ``score_fn(q) -> (len(q), 1)`` is ``checker.rbf_score``; ``fk`` the robot's feature map;
+    Adam with default betas on all waypoints, ``p.grad[~mask] = 0`` before the update, ``robot.wrap`` after it, early
+    exit once the constraint loss of the waypoints BEFORE the update is <= 0.5.  Returns (waypoints, steps taken)."""
+    p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=lr)
+    steps = 0
+    for _ in range(maxiter):
+        opt.zero_grad()
+        collision = 0
+        if collision_weight != 0:
+            check_p = dense_path(p, max_step=max_speed) if dense_check else p  # optim.py:709
+            collision = torch.clamp(score_fn(check_p) + safety_bias, min=0).mean() * len(p)  # optim.py:710-711
+        cp = fk(p)
+        seg = (cp[1:] - cp[:-1]).square()
+        max_move = torch.clamp(seg.sum(dim=2) - max_speed**2, min=0).sum() if max_move_weight != 0 else 0  # :716-718
+        joint_limit = 0
+        if joint_limit_weight != 0:
+            joint_limit = (torch.clamp(limits[:, 0] - p, min=0) + torch.clamp(p - limits[:, 1], min=0)).sum()  # :721-723
+        constraint = collision_weight * collision + max_move_weight * max_move + joint_limit_weight * joint_limit
+        loss = dif_weight * seg.sum() + constraint  # optim.py:726-733
+        loss.backward()
+        if mask is not None:
+            p.grad[~mask] = 0.0
+        opt.step()
+        p.data = wrap_fn(p.data)
+        steps += 1
+        if float(constraint.detach() if torch.is_tensor(constraint) else constraint) <= 0.5:  # optim.py:747
+            break
+    return p.detach(), steps

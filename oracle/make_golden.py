@@ -264,12 +264,50 @@ def gen_optim_replay(ns):
     np.savez_compressed(os.path.join(OUT, "optim_replay.npz"), **out)
 
 
+def gen_weighted(ns):
+    """The reference's ``Weighted.step`` (optim.py:686-761) on a Baxter arm (the only FK classes whose ``fkine`` takes the
+    ``reuse=`` argument that method passes), with and without ``dense_check``.  The current ``DiffCo`` has no
+    ``rbf_score``, so the harness binds the alias the method looks up.  On the CPU the method's
+    ``path_history`` entries all alias the final tensor (``p.cpu()`` is ``p``), so only the final path and the number of
+    iterations are recorded."""
+    M, K, P, OPT = ns.model, ns.kernel, ns.kernel_perceptrons, ns.optim
+    g = torch.Generator().manual_seed(43)
+    robot = M.BaxterLeftArmFK()
+    lim = robot.limits.double()
+    X = torch.rand(900, 7, generator=g, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+    cp = robot.fkine(X)
+    y = ((cp - torch.tensor([0.6, 0.4, 0.3], dtype=cp.dtype)).norm(dim=2) < 0.35).any(1).double() * 2 - 1
+    dc = P.DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+    dc.train(X, y, max_iteration=len(X))
+    dc.fit_poly(K.Polyharmonic(1, 1.0), target="label")
+    dc.rbf_score = dc.poly_score
+    idx = torch.tensor([int(torch.where((X == sp).all(1))[0][0]) for sp in dc.support_points])
+    init = torch.from_numpy(np.linspace(X[0].numpy(), X[1].numpy(), 12))
+    mask = torch.ones(12, dtype=torch.bool)
+    mask[[0, -1]] = False
+    out = {"X": _np(X), "y": _np(y), "idx": _np(idx), "gains": _np(dc.gains), "nodes": _np(dc.rbf_nodes),
+           "support_points": _np(dc.support_points), "init": _np(init), "mask": _np(mask),
+           "maxiter": np.array(25), "weights": np.array([10.0, 10.0, 10.0]), "safety_bias": np.array(0.3),
+           "max_speed": np.array(0.3), "lr": np.array(0.05)}
+    for dense in (False, True):
+        options = {"n_waypoints": 12, "maxiter": 25, "history": True, "max_move_weight": 10, "collision_weight": 10,
+                   "joint_limit_weight": 10, "safety_bias": 0.3, "max_speed": 0.3, "optimizer": torch.optim.Adam,
+                   "optimizer_params": {"lr": 0.05}, "dense_check": dense}
+        res = OPT.Weighted(robot, dc, options).step(init.clone(), mask=mask)
+        out[f"x_dense{int(dense)}"] = _np(res.x)
+        out[f"steps_dense{int(dense)}"] = np.array(len(res.misc["path_history"]))
+    np.savez_compressed(os.path.join(OUT, "weighted.npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(4)
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load_legacy()
-    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay):
+    only = sys.argv[1:]
+    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay, gen_weighted):
+        if only and fn.__name__ not in only:
+            continue
         fn(ns)
         print("wrote", fn.__name__)
 

@@ -152,3 +152,28 @@ def test_adam_traj_optimize_graphed_matches_autograd_and_reference(problem):
     assert np.abs(np.array(rec["solution"]) - g["adam_solution"]).max() <= 1e-4
     with pytest.raises(ValueError):
         OPT.adam_traj_optimize(robot, lambda q: dc.poly_score(q), start, target, dict(opts, init_solution=init.clone(), fused=True))
+
+
+@pytest.mark.parametrize("mode", ["autograd", "autograd_dense", "graphed"])
+def test_weighted_step_matches_the_reference_record(mode, cuda_device):
+    """Weighted.step on the CUDA path against the waypoints the UNMODIFIED reference's Weighted.step produced
+    (tests/golden/weighted.npz: Baxter arm, float64, 25 Adam iterations, with and without dense_check)."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+    from diffco_b200 import optim as OPT
+
+    g = np.load(os.path.join(GOLD, "weighted.npz"))
+    robot = P.make_robot("baxter")
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
+    dc.train(T64(g["X"]), T64(g["y"]), max_iteration=len(g["X"]))
+    assert dc.support_index.tolist() == g["idx"].tolist()
+    dc.fit_poly(K.Polyharmonic(1, 1.0), target="label")
+    dense = mode == "autograd_dense"
+    cw, mmw, jlw = (float(v) for v in g["weights"])
+    options = {"n_waypoints": 12, "maxiter": int(g["maxiter"]), "history": True, "max_move_weight": mmw, "collision_weight": cw,
+               "joint_limit_weight": jlw, "safety_bias": float(g["safety_bias"]), "max_speed": float(g["max_speed"]),
+               "optimizer": torch.optim.Adam, "optimizer_params": {"lr": float(g["lr"])}, "dense_check": dense,
+               "fused": mode == "graphed"}
+    res = OPT.Weighted(robot, dc, options).step(T64(g["init"]), mask=torch.from_numpy(g["mask"]))
+    assert len(res.misc["path_history"]) == int(g[f"steps_dense{int(dense)}"])
+    assert P.rel_to_max(res.x, T64(g[f"x_dense{int(dense)}"])) <= 1e-6

@@ -230,6 +230,28 @@ def test_optimizer_replay_queries_match_reference():
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("dense", [False, True])
+def test_weighted_step_loop_matches_reference(dense):
+    """oracle.weighted_step (the restated optim.py:706-752 loop) against the path the reference's Weighted.step produced
+    on the same Baxter model (tests/golden/weighted.npz): same number of iterations, same waypoints."""
+    import math
+
+    g = load("weighted.npz")
+    robot = P.make_robot("baxter")
+    fk = P.oracle_fk(robot)
+    St = fk(T64(g["support_points"]))
+    nodes = T64(g["nodes"])
+    ph = O.KernelSpec("polyharmonic", 1.0, 1)
+    cw, mmw, jlw = (float(v) for v in g["weights"])
+    x, steps = O.weighted_step(
+        T64(g["init"]), fk, lambda q: O.poly_score(q, fk, ph, St, nodes), robot.limits.double(),
+        lambda q: (math.pi + q) % (2 * math.pi) - math.pi, maxiter=int(g["maxiter"]), collision_weight=cw,
+        max_move_weight=mmw, joint_limit_weight=jlw, safety_bias=float(g["safety_bias"]), max_speed=float(g["max_speed"]),
+        lr=float(g["lr"]), dense_check=dense, mask=torch.from_numpy(g["mask"]))
+    assert steps == int(g[f"steps_dense{int(dense)}"])
+    close(x, g[f"x_dense{int(dense)}"], 1e-9)
+
+
 def test_oracle_against_live_reference():
     """Fresh random problem, larger than the fixtures, straight against the imported reference."""
     import warnings
