@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 from time import time
-from typing import Optional
+
 
 import torch
 

@@ -6,8 +6,6 @@ the matching oracle closures (oracle/diffco_oracle.py) parameterised from the ve
 """
 from __future__ import annotations
 
-import math
-
 import torch
 
 from oracle import diffco_oracle as O
