@@ -71,36 +71,53 @@ class PeerExchange:
             raise RuntimeError(f"at most {_lib.DC_MAX_PEERS} ranks")
         self.rows, self.width, self.device = rows, width, device
         self.nbytes = self.FLAG_BYTES + 2 * rows * width * 4
-        self._own = C.c_void_p()
-        handle = _lib.PeerHandle()
-        with torch.cuda.device(device):
-            _lib.check(self.lib.dc_peer_alloc(self.nbytes, C.byref(self._own), C.byref(handle)), "dc_peer_alloc")
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.bytes), group=group)
-        self._opened = []
-        bases = []
-        for r, hb in enumerate(handles):
-            if r == self.rank:
-                bases.append(self._own.value)
-                continue
-            h = _lib.PeerHandle()
-            C.memmove(h.bytes, hb, 64)
-            p = C.c_void_p()
+        self._own, self._opened = C.c_void_p(), []
+        # Every rank walks through the SAME sequence of collectives whatever fails locally (allocation, IPC mapping):
+        # failures are folded into one consensus at the end, which doubles as the "everyone has mapped every buffer"
+        # barrier; then all ranks raise together and the caller falls back to NCCL on all of them.
+        ok, mine = True, None
+        try:
+            handle = _lib.PeerHandle()
             with torch.cuda.device(device):
-                _lib.check(self.lib.dc_peer_open(C.byref(h), C.byref(p)), "dc_peer_open")
-            self._opened.append(p)
-            bases.append(p.value)
+                _lib.check(self.lib.dc_peer_alloc(self.nbytes, C.byref(self._own), C.byref(handle)), "dc_peer_alloc")
+            mine = bytes(handle.bytes)
+        except Exception:
+            ok = False
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        bases = []
+        if ok and all(h is not None for h in handles):
+            try:
+                for r, hb in enumerate(handles):
+                    if r == self.rank:
+                        bases.append(self._own.value)
+                        continue
+                    h = _lib.PeerHandle()
+                    C.memmove(h.bytes, hb, 64)
+                    ptr = C.c_void_p()
+                    with torch.cuda.device(device):
+                        _lib.check(self.lib.dc_peer_open(C.byref(h), C.byref(ptr)), "dc_peer_open")
+                    self._opened.append(ptr)
+                    bases.append(ptr.value)
+            except Exception:
+                ok = False
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError("peer memory (CUDA IPC) is not available on every rank")
         self.flags = _lib.PeerTable()
         self.outs = [_lib.PeerTable(), _lib.PeerTable()]
-        for r, b in enumerate(bases):
-            self.flags.ptr[r] = b
+        for r, base in enumerate(bases):
+            self.flags.ptr[r] = base
             for k in range(2):
-                self.outs[k].ptr[r] = b + self.FLAG_BYTES + k * rows * width * 4
+                self.outs[k].ptr[r] = base + self.FLAG_BYTES + k * rows * width * 4
         self.views = [torch.as_tensor(_DevicePtr(self._own.value + self.FLAG_BYTES + k * rows * width * 4, (rows, width), "<f4"),
                                       device=device) for k in range(2)]
         self.epoch = 0   # barriers so far
         self.steps = 0   # scoring steps so far (selects the buffer)
-        dist.barrier(group=group)  # every rank has mapped every buffer before anyone stores into them
 
     def close(self):
         for p in getattr(self, "_opened", []):
@@ -227,23 +244,10 @@ class ShardedScorer:
         if self._peer is None or self._peer_rows != b:
             if self._peer:
                 self._peer.close()
-            ok = torch.ones(1, dtype=torch.int32)
-            try:
+            try:  # PeerExchange raises on ALL ranks or on none (its constructor ends with a consensus)
                 self._peer = PeerExchange(self.world * b, self.record_width, self.dtype, self.device, self.group)
                 self._peer_rows = b
-            except Exception:
-                self._peer = False
-                ok.zero_()
-            # all ranks must take the same path: anyone's failure disables it everywhere
-            if dist.get_backend(self.group) == "nccl":
-                okd = ok.to(self.device)
-                dist.all_reduce(okd, op=dist.ReduceOp.MIN, group=self.group)
-                ok = okd.cpu()
-            else:
-                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-            if int(ok.item()) == 0:
-                if self._peer:
-                    self._peer.close()
+            except RuntimeError:
                 self._peer = False
                 return None
         return self._peer.score_and_grad(self._fk, self._kfun.desc, self._sv, q_shard.detach().contiguous())

@@ -66,3 +66,28 @@ def test_shard_bounds_cover_the_batch_exactly():
                 assert rows == list(range(total))
             else:
                 assert rows[0][0] == 0 and rows[-1][1] == total and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+
+
+def _peer_failure_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        raised = False
+        try:  # no CUDA device here: allocation fails on every rank -> they must all raise, in step, without hanging
+            D.PeerExchange(64, 8, torch.float32, torch.device("cpu"), dist.group.WORLD)
+        except RuntimeError:
+            raised = True
+        t = torch.tensor([rank + 1.0])
+        dist.all_reduce(t)  # the ranks' collective sequences are still aligned
+        results[rank] = bool(raised and t.item() == world * (world + 1) / 2)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_setup_fails_consistently_without_peer_memory():
+    """The fused all-gather's set-up (diffco_b200/distributed.py::PeerExchange) must degrade on ALL ranks together — the
+    caller then uses NCCL everywhere — and keep the ranks' collectives in step whatever failed locally."""
+    world = 2
+    results = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_peer_failure_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert all(results.get(r) for r in range(world)), dict(results)
