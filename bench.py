@@ -359,6 +359,11 @@ def run_native(args):
                                     ("fused into the kernel epilogue (peer stores over NVLink + flag barrier)"
                                      if getattr(scorer, "_peer", None) else "by one NCCL all_gather_into_tensor")),
                        "gather_check": gather_check,
+                       "arithmetic": ("fp32 in / out; radial profile, score and near pairs in fp32; the two contractions as tcgen05 "
+                                      "kind::f16 MMAs on operands split into two 11-bit terms (products ~22 bits) with fp32 "
+                                      "accumulation; parity vs the float64 oracle equals the FP32-pipe kernel's (1.7e-6 score, "
+                                      "1.8e-6 grad of max on this workload, gate 1e-5; tests/test_gpu_tc.py)"
+                                      if which == 2 else "fp32 throughout (packed FP32 pipe)"),
                        "l2": "flushed before every step (256 MiB memset, untimed" +
                              ("; ranks re-aligned by an untimed device barrier after it" if world > 1 else "") +
                              "); per-step CUDA events summed"},
