@@ -48,23 +48,22 @@ static tq_fn const kTqTable[3][2][2] = {
     {{tq_mq_c1_score, tq_mq_c1_grad}, {tq_mq_c4_score, tq_mq_c4_grad}},
 };
 
-static int device_sm_count(int* out) {
-  static int cached_dev = -1, cached_sms = 0;
+int device_sm_count(int* out) {
+  static std::atomic<int> cached[64];  // per device ordinal; 0 = not queried yet (thread-safe: worst case two queries)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {
     (void)cudaGetLastError();
     return DC_ERR_NO_DEVICE;
   }
-  if (dev != cached_dev) {
-    int sms = 0;
+  int sms = (dev >= 0 && dev < 64) ? cached[dev].load(std::memory_order_relaxed) : 0;
+  if (sms == 0) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
       (void)cudaGetLastError();
       return DC_ERR_NO_DEVICE;
     }
-    cached_dev = dev;
-    cached_sms = sms;
+    if (dev >= 0 && dev < 64) cached[dev].store(sms, std::memory_order_relaxed);
   }
-  *out = cached_sms;
+  *out = sms;
   return DC_OK;
 }
 

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/diffco_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -30,6 +32,35 @@ extern long long g_launch_count;  // host-side counter, bumped by every launch w
   } while (0)
 
 constexpr int kWarp = 32;
+
+// Per-device one-time initialisation (cudaFuncSetAttribute is a per-device attribute; one process may score on several
+// GPUs).  One instance per kernel instantiation; doing the initialisation twice from racing threads is harmless.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  // returns the current device ordinal (< 64) in *dev and whether its bit is still clear; -1 on error
+  int pending(int* dev) {
+    if (cudaGetDevice(dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return -1;
+    }
+    if (*dev < 0 || *dev >= 64) return 1;  // never cached: always initialise
+    return (done.load(std::memory_order_acquire) >> *dev) & 1ull ? 0 : 1;
+  }
+  void mark(int dev) {
+    if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
+#define DC_SET_FUNC_ATTR_ONCE(kern, attr, value)                         \
+  do {                                                                   \
+    static dc::PerDeviceOnce _once;                                      \
+    int _dev = 0;                                                        \
+    const int _p = _once.pending(&_dev);                                 \
+    if (_p < 0) return DC_ERR_NO_DEVICE;                                 \
+    if (_p > 0) {                                                        \
+      DC_CUDA_OK(cudaFuncSetAttribute(kern, attr, value));               \
+      _once.mark(_dev);                                                  \
+    }                                                                    \
+  } while (0)
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -868,11 +868,7 @@ int launch_score_tc(TcArgs& a, int num_sms, cudaStream_t stream) {
   const int grid = (int)min((long long)2 * num_sms, (long long)a.n_tiles);
   if (((long long)a.n_tiles / grid + 1) * a.n_chunks >= (1LL << 31) || a.n_sv >= (1 << 24)) return DC_ERR_UNSUPPORTED;
   auto kern = score_tc_kernel<MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SM_BYTES));
-    attr_set = true;
-  }
+  DC_SET_FUNC_ATTR_ONCE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SM_BYTES);
   kern<<<grid, L::THREADS, L::SM_BYTES, stream>>>(a);
   DC_LAUNCH_CHECK();
   return DC_OK;

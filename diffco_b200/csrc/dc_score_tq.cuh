@@ -365,11 +365,7 @@ int launch_score_tq(ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
   a.n_tiles = (int)ceil_div64(a.batch, Cfg::QT);
   const size_t smem = Cfg::smem_bytes(ch);
   auto kern = score_tq_kernel<F, KIND, CW, MODE, NWG, STAGES>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    DC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    attr_set = true;
-  }
+  DC_SET_FUNC_ATTR_ONCE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);  // per instantiation, per device
   const int grid = (int)min((long long)num_sms, (long long)ceil_div64(a.n_tiles, Cfg::NGRP));
   kern<<<grid, 512, smem, stream>>>(a);
   DC_LAUNCH_CHECK();

@@ -173,11 +173,7 @@ static int launch_traj_step(const dc_fk_desc* fk, const dc_traj_params* prm, int
   const size_t smem = sizeof(T) * ((size_t)n_wp * a.n_feat + 40);
   if (smem > 200 * 1024) return DC_ERR_UNSUPPORTED;
   auto kern = traj_step_kernel<T>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  DC_SET_FUNC_ATTR_ONCE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   kern<<<1, 256, smem, stream>>>(a);
   DC_LAUNCH_CHECK();
   return DC_OK;

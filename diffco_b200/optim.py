@@ -102,7 +102,7 @@ def adam_traj_optimize(robot, dist_est, start_cfg, target_cfg, options):
             return _trivial_record(robot, path, start_cfg, target_cfg, seed, t0)
         if options.get("fused", False):
             checker, weights = target
-            if stepper is None:
+            if stepper is None or stepper.p.shape != path.shape:  # init_solution may have a different length than N_WAYPOINTS
                 mask = torch.ones(len(path), dtype=torch.bool)
                 mask[[0, -1]] = False  # the end points are fixed
                 stepper = trajopt.GraphedPenaltyStep(robot, checker, weights, path.to(checker.device), mask,

@@ -58,7 +58,10 @@ def dense_path(q, max_step=2.0, max_step_num=None):
     k = (torch.arange(len(seg_index), device=q.device) - first.to(q.device)[seg_index]).to(q.dtype).reshape(-1, 1)
     delta = q[1:] - q[:-1]
     dist = delta.norm(dim=-1, keepdim=True)
-    pts = q[:-1][seg_index] + k * (delta * max_step / dist)[seg_index]
+    # a zero-length segment contributes no points (steps == 0): keep its 0/0 direction out of the autograd graph
+    # (the reference's per-segment loop never evaluates it, utils.py:93-99)
+    unit = delta * max_step / torch.where(dist > 0, dist, torch.ones_like(dist))
+    pts = q[:-1][seg_index] + k * unit[seg_index]
     dense = torch.cat([pts, q[-1:]])
     assert torch.all(dense[0] == q[0]) and torch.all(dense[-1] == q[-1])
     return dense
