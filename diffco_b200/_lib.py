@@ -20,7 +20,7 @@ DC_MAX_TOOL_POINTS = 2
 DC_MAX_FEATURES = 64
 DC_MAX_CLASSES = 8
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DC_F32, DC_F64 = 0, 1
 DC_FK_NONE, DC_FK_PLANAR_CHAIN, DC_FK_SE2_BODY, DC_FK_SE3_BODY, DC_FK_DH_ARMS, DC_FK_SE2_BASE_PLANAR_ARM = range(6)
 DC_K_RQ, DC_K_POLYHARMONIC, DC_K_MULTIQUADRIC = 1, 2, 3
@@ -81,6 +81,7 @@ class Supports(C.Structure):
         ("reserved", C.c_int32),
         ("tc_blob", C.c_void_p),
         ("tc_s2max", C.c_double),
+        ("tc_gamma", C.c_double),
     ]
 
 
@@ -105,7 +106,7 @@ class TrajParams(C.Structure):
     ]
 
 
-DC_OPT_TC_ENABLE, DC_OPT_TC_ERR_COEF, DC_OPT_TC_TOL_PAIR, DC_OPT_TC_MIN_BATCH = 1, 2, 3, 4
+DC_OPT_TC_ENABLE, DC_OPT_TC_ERR_COEF, DC_OPT_TC_TOL_PAIR, DC_OPT_TC_MIN_BATCH, DC_OPT_TC_STATS, DC_OPT_PEER_TIMEOUT_S = 1, 2, 3, 4, 5, 6
 KERNEL_NAMES = {0: "lane-split", 1: "thread-per-query", 2: "tensor-core", -1: "none"}
 
 
@@ -117,7 +118,8 @@ PROTOTYPES = {
     "dc_supports_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dc_pack_supports": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_supports_tc_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
-    "dc_pack_supports_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_pack_supports_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(KernelDesc), C.c_void_p, C.c_void_p]),
+    "dc_supports_tc_info": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "dc_set_option": (C.c_int, [C.c_int32, C.c_double]),
     "dc_get_option": (C.c_double, [C.c_int32]),
     "dc_last_score_kernel": (C.c_int, []),

@@ -8,9 +8,12 @@
 
 namespace dc {
 
+double g_peer_timeout_s = 120.0;  // DC_OPT_PEER_TIMEOUT_S
+
 // Thread r: tell rank r that this rank has finished epoch `epoch` (release, system scope), then wait until rank r has
 // told us the same (acquire).  Launched after the kernel whose peer stores it publishes, on the same stream.
-__global__ void __launch_bounds__(32) peer_barrier_kernel(dc_peer_table flags, int rank, int world, uint32_t epoch) {
+__global__ void __launch_bounds__(32) peer_barrier_kernel(dc_peer_table flags, int rank, int world, uint32_t epoch,
+                                                          long long timeout_cycles) {
   const int r = threadIdx.x;
   if (r >= world) return;
   __threadfence_system();
@@ -22,7 +25,9 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(dc_peer_table flags, i
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
     if ((int32_t)(v - epoch) >= 0) break;
-    if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a rank died
+    // a rank that never arrives (it died, or its launch failed) must not hang the GPU for ever: after the configured
+    // time (default 120 s — host-side skew such as a first-call build or data loading is far below that) give up
+    if (clock64() - t0 > timeout_cycles) __trap();
   }
 }
 
@@ -87,7 +92,8 @@ int dc_peer_barrier(const dc_peer_table* flags, int32_t rank, int32_t world, uin
   if (!flags || world < 1 || world > DC_MAX_PEERS || rank < 0 || rank >= world) return DC_ERR_INVALID_ARG;
   for (int r = 0; r < world; ++r)
     if (!flags->ptr[r]) return DC_ERR_INVALID_ARG;
-  dc::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*flags, rank, world, epoch);
+  const long long cycles = (long long)(dc::g_peer_timeout_s * 2.0e9);
+  dc::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*flags, rank, world, epoch, cycles);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

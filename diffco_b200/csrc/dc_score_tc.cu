@@ -6,11 +6,14 @@
 
 namespace dc {
 
+extern double g_peer_timeout_s;  // dc_peer.cu
+
 // process-wide knobs (dc_set_option)
 static double g_tc_enable = -1.0;  // -1: not initialised (reads DIFFCO_B200_TC once)
 static double g_tc_err_coef = 5e-7;
 static double g_tc_tol_pair = 2e-7;
 static double g_tc_min_batch = 4096;
+static unsigned long long* g_tc_stats = nullptr;  // device counter of near pairs (DC_OPT_TC_STATS), lazily allocated
 
 static bool tc_enabled() {
   if (g_tc_enable < 0) {
@@ -26,6 +29,21 @@ int tc_set_option(int option, double value) {
     case DC_OPT_TC_ERR_COEF: if (!(value > 0)) return DC_ERR_INVALID_ARG; g_tc_err_coef = value; return DC_OK;
     case DC_OPT_TC_TOL_PAIR: if (!(value > 0)) return DC_ERR_INVALID_ARG; g_tc_tol_pair = value; return DC_OK;
     case DC_OPT_TC_MIN_BATCH: if (!(value >= 1)) return DC_ERR_INVALID_ARG; g_tc_min_batch = value; return DC_OK;
+    case DC_OPT_PEER_TIMEOUT_S: if (!(value > 0)) return DC_ERR_INVALID_ARG; g_peer_timeout_s = value; return DC_OK;
+    case DC_OPT_TC_STATS: {
+      // value != 0: start (or reset) counting the pairs the tensor-core kernel re-evaluates exactly; 0: stop
+      if (value == 0.0) {
+        if (g_tc_stats) (void)cudaFree(g_tc_stats);
+        g_tc_stats = nullptr;
+        return DC_OK;
+      }
+      if (!g_tc_stats && cudaMalloc(&g_tc_stats, sizeof(unsigned long long)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        g_tc_stats = nullptr;
+        return DC_ERR_CUDA;
+      }
+      return cudaMemset(g_tc_stats, 0, sizeof(unsigned long long)) == cudaSuccess ? DC_OK : DC_ERR_CUDA;
+    }
     default: return DC_ERR_INVALID_ARG;
   }
 }
@@ -35,6 +53,16 @@ double tc_get_option(int option) {
     case DC_OPT_TC_ERR_COEF: return g_tc_err_coef;
     case DC_OPT_TC_TOL_PAIR: return g_tc_tol_pair;
     case DC_OPT_TC_MIN_BATCH: return g_tc_min_batch;
+    case DC_OPT_PEER_TIMEOUT_S: return g_peer_timeout_s;
+    case DC_OPT_TC_STATS: {  // synchronises the device: a debugging / test facility
+      if (!g_tc_stats) return -1.0;
+      unsigned long long v = 0;
+      if (cudaMemcpy(&v, g_tc_stats, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return NAN;
+      }
+      return (double)v;
+    }
     default: return NAN;
   }
 }
@@ -52,6 +80,8 @@ bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel
   const int F = fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim;
   if (!tc_shape_ok(F, sv.n_class, sv.dtype) || fk.dof > DC_MAX_DOF) return false;
   if (kernel.kind != DC_K_RQ || kernel.order != 2 || !(kernel.param > 0)) return false;
+  if ((float)kernel.param != (float)sv.tc_gamma) return false;  // the operand image has the kernel width folded in
+  if (fk.type != DC_FK_NONE && fk.dof > TcLayout::QS_DOF) return false;
   if (grad_mode != DC_GRAD_NONE && grad_mode != DC_GRAD_SUM) return false;
   if (batch < (int64_t)g_tc_min_batch || sv.n >= (1 << 24)) return false;
   if (sv.tc_s2max > 0) {
@@ -80,6 +110,7 @@ int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
   a.grad_out = (grad_mode == DC_GRAD_SUM) ? static_cast<const float*>(grad_out) : nullptr;
   a.trace = nullptr;
   a.dbg = nullptr;
+  a.stats = g_tc_stats;
   a.batch = batch;
   a.score_ld = score_ld;
   a.grad_ld = grad_ld;
@@ -109,11 +140,25 @@ int dc_supports_tc_bytes(int64_t n, int32_t n_features, int32_t n_class, int32_t
   return DC_OK;
 }
 
-int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_features, void* blob, dc_stream_t stream) {
-  if (n < 1 || !s_feat || !w || !blob || (reinterpret_cast<uintptr_t>(blob) & 127) != 0) return DC_ERR_INVALID_ARG;
+int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_features, const dc_kernel_desc* kernel,
+                        void* blob, dc_stream_t stream) {
+  if (n < 1 || !s_feat || !w || !blob || !kernel || (reinterpret_cast<uintptr_t>(blob) & 127) != 0) return DC_ERR_INVALID_ARG;
   if (!tc_shape_ok(n_features, 1, DC_F32) || n >= (1 << 24)) return DC_ERR_UNSUPPORTED;
+  if (kernel->kind != DC_K_RQ || kernel->order != 2 || !(kernel->param > 0)) return DC_ERR_UNSUPPORTED;
   return launch_pack_supports_tc(static_cast<const float*>(s_feat), static_cast<const float*>(w), n, n_features,
-                                 static_cast<unsigned char*>(blob), (cudaStream_t)stream);
+                                 (float)kernel->param, static_cast<unsigned char*>(blob), (cudaStream_t)stream);
+}
+
+int dc_supports_tc_info(const void* blob, int64_t n, double* s2max, int32_t* valid) {
+  if (!blob || n < 1 || n >= (1 << 24)) return DC_ERR_INVALID_ARG;
+  float t[TcLayout::TRAILER_FLOATS];
+  if (cudaMemcpy(t, tc_trailer(blob, n), sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) {  // synchronises (pack time)
+    (void)cudaGetLastError();
+    return DC_ERR_CUDA;
+  }
+  if (s2max) *s2max = (double)t[0];
+  if (valid) *valid = t[8] != 0.f ? 1 : 0;
+  return DC_OK;
 }
 
 int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,

@@ -1,36 +1,34 @@
 // Fused collision-score kernel, tensor-core form (tcgen05 + TMEM + bulk TMA; RQKernel(p = 2), one class, fp32 I/O, F <= 14).
 //
-//   score[b] = sum_n w_n k(rho_bn)        g_x[b] = -2 gamma sum_n w_n u^3 (x_b - s_n)        rho_bn = |x_b - s_n|^2
+//   score[b] = sum_n w_n u_bn^2      g_x[b] = -2 gamma sum_n w_n u_bn^3 (x_b - s_n)      u = 1 / (1 + gamma/2 |x_b - s_n|^2)
 //
 // Same contract as score_tq_kernel (dc_score_tq.cuh) for diffco/kernel_perceptrons.py:362-370 (DiffCo.score with
 // diffco/kernel.py:17-29 and a diffco/model.py feature map) and its autograd backward, but the two contractions run on
 // the 5th-generation tensor cores instead of the FP32 pipe:
 //
-//   GEMM1  rho[128 x 96]  = A[128 x 48] . B1[96 x 48]^T     (kind::f16, K = 48 = 3 x 16 slots, fp32 accumulate in TMEM)
-//   GEMM2  G  [128 x 32] += CC[128 x 16] . B2[32 x 16]^T    per 8 support vectors, CC read from TMEM
+//   GEMM1  T [128 x 96]  = A[128 x 48] . B1[96 x 48]^T      T = tau (1 + gamma/2 rho): kernel width and the "+1" are folded
+//                                                           into the operands (kind::f16, K = 3 x 16 slots, fp32 in TMEM)
+//   GEMM2  G [128 x 32] += CC[128 x 16] . B2[32 x 16]^T     per 8 support vectors, CC = 2^15 u^3 read from TMEM, the
+//                                                           weights folded into B2 = [w s | w]
 //
-// Every fp32 quantity enters as a sum of 11-bit terms (x = xh + xl, s = sh + sl, cc = ch + cl) placed in separate K slots:
-//   rho = sum_f xh(-2sh) + xl(-2sh) + xh(-2s)_l  +  |s|^2 (3 terms x 1) + |x|^2 (3 terms x 1)          48 slots
-//   G[:, 0:16]  = sum_n (ch + cl) [sh | 1]          G[:, 16:32] = sum_n ch sl        g_x = -2 gamma (x G[14] - G[f] - G[16+f])
-// i.e. products carry ~22 bits and are accumulated in fp32.  Power-of-two scales (features by Sx, weights by Sw, chosen
-// at pack time) keep every term inside fp16's exponent range and are undone exactly in the epilogue.
-// The expansion |x|^2 + |s|^2 - 2 x.s leaves an ABSOLUTE error of ~1e-5 (scaled by the feature magnitudes) in rho, which
-// matters only where k'(rho) is large, i.e. for the few pairs with small rho: those (rho below a per-query threshold
-// derived from the error bound) are re-evaluated exactly with direct differences on the FP32 pipe and removed from the
-// tensor-core sums.  Every other pair's error is below tol_pair (2e-7) of its weight.
+// Every fp32 quantity enters as a sum of 11-bit terms in separate K slots (x = xh + xl, s = sh + sl, cc = ch + cl), so
+// products carry ~22 bits and are accumulated in fp32.  Power-of-two scales keep every term inside fp16's range and are
+// undone exactly in the epilogue.  The expansion |x|^2 + |s|^2 - 2 x.s leaves an ABSOLUTE error in rho that scales with
+// the feature norms (the tensor core aligns its addends to the largest one); it only matters where k'(rho) is large, i.e.
+// for the few pairs with small rho: pairs under a per-(query, chunk) threshold derived from the error bound are taken
+// out of the tensor-core sums and evaluated exactly with direct differences on the FP32 pipe.
 //
-// One tcgen05.mma occupies the tensor pipe for >= ~85 cycles whatever its N (profiles/r01c_umma_issue_cost.txt), so the
-// instruction count per support vector is what bounds this kernel: 3 instructions per 96 supports for GEMM1 and one
-// per 8 supports for GEMM2 (the K-slot packing above exists to get there).
-//
-// CTA = 256 query threads (8 warps: TMEM lane quarter = warp & 3 <-> 32 queries of the tile, column half = warp >> 2)
-// + 1 control warp; two CTAs per SM.
-//   control warp: one elected lane streams 21.4 KB support "blobs" (pre-arranged UMMA operand images written by
-//                 pack_supports_tc_kernel) L2 -> smem with 1-D bulk TMA through a 3-slot ring, issues GEMM1(j) and
-//                 GEMM2(j-1) and signals completion with tcgen05.commit -> mbarrier;
-//   query threads: FK -> A operand into shared memory; per chunk tcgen05.ld rho (96 columns), radial profile with packed
-//                 FP32 (FFMA2/FMUL2) + MUFU.RCP, score in registers, coefficients split, packed to f16x2 and written back
-//                 with tcgen05.st over the rho columns; epilogue tcgen05.ld G, J_FK^T, coalesced store.
+// CTA = 8 query warps + 4 service warps, two CTAs per SM, persistent over a contiguous range of 128-query tiles.
+//   warp 8   (one elected lane) issues every tcgen05.mma: GEMM2(j) then GEMM1(j+2) — the same thread, so the hardware's
+//            in-order execution covers the TMEM hazards between them; tcgen05.commit -> mbarriers;
+//   warp 9   streams the GEMM1 operand images (9 KB per 96 supports) L2 -> smem, 2-slot ring, 1-D bulk TMA;
+//   warp 10  streams the GEMM2 operand images (12 KB), 2-slot ring; the fp32 weights come from L1;
+//   query warps: TMEM lane quarter = warp & 3 <-> 32 queries of the tile, column half = warp >> 2.  Per chunk:
+//            tcgen05.ld T (48 columns) -> near test -> packed FP32 (FMUL2/FFMA2), one MUFU.RCP per column PAIR -> score in
+//            registers, coefficients split, cvt.rn.f16x2, tcgen05.st over the T columns -> arrive.
+//   Tiles are software-pipelined across the two halves of the query warps: while the upper half (owners) runs tile t's
+//   epilogue (G from TMEM, J_FK^T, records), the lower half already runs forward kinematics and builds the A operand of
+//   tile t+1 and enters its chunk loop; G is double-buffered in TMEM for that.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -46,54 +44,60 @@ struct TcLayout {
   static constexpr int NC = 96;    // support vectors per chunk == UMMA N of GEMM1
   static constexpr int FMAX = 14;  // features
   static constexpr int K1 = 48;    // GEMM1 K slots
-  static constexpr int N2 = 32;    // GEMM2 N: [14 features, sum(cc), 0 | 14 feature corrections, 0, 0]
+  static constexpr int N2 = 32;    // GEMM2 N: [w s (14), w, 0 | corrections (14), w correction, 0]
   static constexpr int ONES_ROW = 14;
   static constexpr int KS2 = NC / 8;  // GEMM2 instructions per chunk (8 supports x {ch, cl} each)
-  // blob (bytes)
-  static constexpr int B1_BYTES = NC * K1 * 2;        // [K1/8][NC][8] f16          9216
-  static constexpr int B2_STEP_BYTES = N2 * 16 * 2;   // per 8 supports: [2][32][8]   1024
-  static constexpr int OFF_B1 = 0;
-  static constexpr int OFF_B2 = OFF_B1 + B1_BYTES;
-  static constexpr int OFF_W = OFF_B2 + KS2 * B2_STEP_BYTES;  // 21504
-  static constexpr int BLOB_BYTES = OFF_W + NC * 4;            // 21888 = 171 x 128
-  static constexpr int TRAILER_FLOATS = 8;  // {max|s|^2, max|w| (bit patterns, atomicMax), Sx, 1/Sx, Sw, 1/Sw, 0, 0}
-  static constexpr int RS = 3;              // ring slots
-  // TMEM columns
-  static constexpr int COL_STAGE = NC;      // per stage: rho, overwritten in place by the packed coefficients
-  static constexpr int COL_G = 2 * COL_STAGE;  // 192 .. 223
+  // operand images (bytes).  Global layout: [n_chunks x B1][n_chunks x B2][weights n_chunks x NC f32][chunk max|s|^2,
+  // n_chunks f32 padded to a multiple of 4][trailer].  The weights and chunk maxima are read straight from global memory
+  // (warp-uniform 16-byte loads, L1-resident: 8 KB for 2000 supports), so the query warps never wait for the GEMM2 image.
+  static constexpr int B1_BYTES = NC * K1 * 2;        // [K1/8][NC][8] f16           9216
+  static constexpr int B2_STEP_BYTES = N2 * 16 * 2;   // per 8 supports: [2][32][8]  1024
+  static constexpr int B2_BYTES = KS2 * B2_STEP_BYTES;  // 12288
+  // trailer floats: 0 max|s|^2 (bits, atomicMax)  1 max |w| max(1, |s_f|) (bits)  2 max |s_f| (bits)
+  //                 3 Sa  4 tau c0  5 tau  6 1/(2^15 Sg)  7 gamma  8 valid (1.0 / 0.0)  9 1/(tau c0)
+  static constexpr int TRAILER_FLOATS = 16;
+  static constexpr int RS1 = 2, RS2 = 2;    // ring slots (both indexed by chunk parity, like the TMEM stages)
+  // TMEM columns: two T / CC stages, two G accumulators (tile parity)
+  static constexpr int COL_STAGE = NC;
+  static constexpr int COL_G = 2 * COL_STAGE;  // 192 .. 223, 224 .. 255
   static constexpr int TMEM_COLS = 256;
-  // shared memory (bytes)
-  static constexpr int SM_BAR = 0;  // mbarriers
-  static constexpr int SM_TMEM_SLOT = 128;
-  static constexpr int SM_RING = 256;
-  static constexpr int SM_A = SM_RING + RS * BLOB_BYTES;       // A [K1/8][128][8] f16
-  static constexpr int QCAP = 128;                             // near-pair queue entries per warp
-  static constexpr int QWARPS = 8;                             // query warps: 4 TMEM lane quarters x 2 column halves
+  static constexpr int QCAP = 64;    // near-pair queue entries per warp
+  static constexpr int QWARPS = 8;   // query warps: 4 TMEM lane quarters x 2 column halves
   static constexpr int QTHREADS = QWARPS * 32;
   static constexpr int CTRL_WARP = QWARPS;
-  static constexpr int THREADS = QTHREADS + 128;  // + the control warpgroup: warp 8 works, warps 9..11 only donate registers
-  static constexpr int SM_XS = SM_A + TM * K1 * 2;             // features of the tile [128][16] f32 (near-pair path)
-  // one region, three lives per tile: staged q [128][16] -> per-warp exact accumulators (feature gradient
-  // [8][32][16] + score [8][32]) -> output records [128][17]
-  static constexpr int SM_GEX = SM_XS + TM * 16 * 4;
-  static constexpr int SM_QS = SM_GEX;
-  static constexpr int GEX_BYTES = QWARPS * 32 * 17 * 4;        // 17408 >= TM * (DC_MAX_DOF + 1) * 4
-  static constexpr int SM_ROWS = SM_GEX + GEX_BYTES;            // partial scores, thresholds [2][128]
-  static constexpr int SM_QUEUE = SM_ROWS + 2 * TM * 4;
+  static constexpr int THREADS = QTHREADS + 128;
+  static constexpr int QS_DOF = 8;   // staged configurations: dof <= 8 for real feature maps (FK NONE needs none)
+  // shared memory (bytes)
+  static constexpr int SM_BAR = 0;
+  static constexpr int SM_TMEM_SLOT = 192;
+  static constexpr int SM_RING1 = 256;
+  static constexpr int SM_RING2 = SM_RING1 + RS1 * B1_BYTES;
+  static constexpr int SM_A = SM_RING2 + RS2 * B2_BYTES;    // A [K1/8][128][8] f16
+  static constexpr int SM_XS = SM_A + TM * K1 * 2;          // features [2][128][16] f32 (near-pair path, epilogue)
+  // exact-path accumulators: score [8][32], feature gradient [8][32][16] (non-owner warps first); the owners' half
+  // (+ 512 bytes) doubles as the output records [128][17] once the owners have read it
+  static constexpr int SM_ACC = SM_XS + 2 * TM * 16 * 4;
+  static constexpr int ACC_BYTES = QWARPS * 32 * 4 + QWARPS * 32 * 16 * 4 + 512;
+  static constexpr int SM_QS = SM_ACC + ACC_BYTES;          // staged configurations [2][128][QS_DOF]
+  static constexpr int SM_ROWS = SM_QS + 2 * TM * QS_DOF * 4;  // lower-half partial scores [128], |x|^2 [2][128]
+  static constexpr int SM_QUEUE = SM_ROWS + 3 * TM * 4;
   static constexpr int SM_BYTES = SM_QUEUE + QWARPS * QCAP * 4;
 };
+static_assert(2 * (TcLayout::SM_BYTES + 1024) <= 233472, "two CTAs per SM must fit in 228 KB of shared memory");
+static_assert(TcLayout::TM * (DC_MAX_DOF + 1) * 4 <= 4 * 32 * 16 * 4 + 512, "output records must fit the owners' accumulators");
 
 struct TcArgs {
   dc_fk_desc fk;
   RadialConsts<float> rc;
-  const unsigned char* blob;  // n_chunks x BLOB_BYTES + trailer
+  const unsigned char* blob;  // [n_chunks x B1][n_chunks x B2][weights][chunk max|s|^2][trailer]
   const float* table;         // packed [-s | w] rows (dc_pack_supports), for the exact near-pair path
   const float* q;
   float* score;
   float* grad;
   const float* grad_out;
-  long long* trace;  // optional clock64 timeline of CTA 0 (tools/probe/tc_probe.cu), 16 slots per chunk
-  float* dbg;  // optional debug dump (tools/probe/tc_probe.cu): tile 0 rho [128][n_chunks*NC] then G [128][32]
+  long long* trace;  // optional clock64 timeline (tools/probe/tc_probe.cu), 16 slots per chunk
+  float* dbg;        // optional debug dump (tools/probe/tc_probe.cu): tile 0 rho [128][n_chunks*NC] then G [128][32], x [128][16]
+  unsigned long long* stats;  // optional: [0] += near pairs evaluated exactly
   long long batch;
   long long score_ld;
   long long grad_ld;
@@ -106,7 +110,7 @@ struct TcArgs {
   int n_chunks;
   float* bcast[DC_MAX_PEERS];  // n_bcast > 0: every fused record block is stored into each of these (row 0 = row 0 of the
   int n_bcast;                 // gathered buffer; `score` then points at THIS rank's block of the first one)
-  float err_coef;  // delta(rho) <= err_coef * (|x|^2 + max|s|^2)
+  float err_coef;  // delta(rho) <= err_coef * (|x|^2 + max_chunk |s|^2)
   float tol_pair;  // admissible |w|-relative error of one pair
 };
 
@@ -237,46 +241,72 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 }
 __device__ __forceinline__ float pow2_floor(float v) { return __uint_as_float(__float_as_uint(v) & 0x7f800000u); }
 
-// ---- pack: support vectors -> chunk blobs ----------------------------------------------------------------------
-// trailer[0], trailer[1] = max |s|^2, max |w| (as int bit patterns; zeroed by the caller before this kernel)
+// ---- pack: support vectors -> operand images ----------------------------------------------------------------------
+// trailer[0..2] = max |s|^2, max |w| max(1, max_f |s_f|), max |s_f| (as int bit patterns; zeroed by the caller)
 __global__ void __launch_bounds__(128) tc_scan_kernel(const float* __restrict__ s, const float* __restrict__ w, int n, int F,
                                                         int* __restrict__ trailer) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float ss = 0.f;
-  for (int f = 0; f < F; ++f) ss = fmaf(s[(size_t)i * F + f], s[(size_t)i * F + f], ss);
+  float ss = 0.f, sm = 0.f;
+  for (int f = 0; f < F; ++f) {
+    const float v = s[(size_t)i * F + f];
+    ss = fmaf(v, v, ss);
+    sm = fmaxf(sm, fabsf(v));
+  }
   atomicMax(&trailer[0], __float_as_int(ss));
-  atomicMax(&trailer[1], __float_as_int(fabsf(w[i])));
+  atomicMax(&trailer[1], __float_as_int(fabsf(w[i]) * fmaxf(1.f, sm)));
+  atomicMax(&trailer[2], __float_as_int(sm));
 }
 
-// Power-of-two scales: Sx^2 max|s|^2 <= 2^14 (so every f16 term of the supports is < 2^15), Sw max|w| <= 2^14.
-__device__ __forceinline__ void tc_scales(const float* trailer, float& sx, float& sw) {
-  const float ssmax = trailer[0], wmax = trailer[1];
-  sx = (ssmax > 0.f) ? pow2_floor(sqrtf(16384.f / ssmax)) : 1.f;
-  sw = (wmax > 0.f) ? pow2_floor(16384.f / wmax) : 1.f;
-  sx = fminf(fmaxf(sx, 1.f / 1048576.f), 1048576.f);
-  sw = fminf(fmaxf(sw, 1.f / 1048576.f), 1048576.f);
+// Scales of the operand images for RQKernel(gamma, p = 2).
+//   T = tau (1 + c0 rho), c0 = gamma / 2, tau = 2^-5: u' = 1/T <= 32, k' = u'^2 = 2^10 u^2, cc = u'^3 = 2^15 u^3 <= 2^15 (f16).
+//   A side holds Sa x, B side (-2 tau c0 / Sa) s with Sa the power of two nearest sqrt(2 tau c0): both sides the same size.
+//   GEMM2's B operand holds Sg w [s | 1] with Sg a power of two, Sg max|w s| <= 2^8.
+struct TcScales {
+  float sa, tc0, tau, beta, sg, inv_g;
+  bool valid;
+};
+__device__ __forceinline__ TcScales tc_scales(const float* trailer, float gamma) {
+  TcScales c;
+  const float ssmax = trailer[0], wsmax = trailer[1], sfmax = trailer[2];
+  c.tau = 1.f / 32.f;
+  c.tc0 = c.tau * 0.5f * gamma;
+  c.sa = pow2_floor(sqrtf(2.f * c.tc0) * 1.41421356f);
+  c.sa = fminf(fmaxf(c.sa, 1.f / 4096.f), 4096.f);
+  c.beta = -2.f * c.tc0 / c.sa;
+  c.sg = (wsmax > 0.f) ? pow2_floor(256.f / wsmax) : 1.f;
+  c.sg = fminf(fmaxf(c.sg, 1.f / 1048576.f), 1048576.f);
+  c.inv_g = 1.f / (32768.f * c.sg);
+  // every 11-bit term of the dominant features (and its /256, x256 companions) must be a normal f16 number
+  const float am = c.sa * sfmax, bm = fabsf(c.beta) * sfmax;
+  c.valid = gamma > 0.f && am <= 8192.f && bm <= 8192.f && am >= 1.f / 64.f && bm >= 1.f / 64.f &&
+            (c.tau + c.tc0 * ssmax) <= 30000.f && wsmax > 0.f && c.sg * wsmax <= 512.f;
+  return c;
 }
 
-// One thread per (chunk, local support index).  s_feat[N, F] are the transformed supports, w[N] the weights.
+// One thread per (chunk, local support index).  s_feat[N, F] are the transformed supports, w[N] the weights.  The whole
+// blob was zeroed by the caller (the chunk maxima are accumulated with atomicMax).
 __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __restrict__ s, const float* __restrict__ w,
-                                                                 int n, int F, int n_chunks, unsigned char* __restrict__ blob) {
+                                                                 int n, int F, int n_chunks, float gamma,
+                                                                 unsigned char* __restrict__ blob) {
   using L = TcLayout;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_chunks * L::NC) return;
-  float* trailer = reinterpret_cast<float*>(blob + (size_t)n_chunks * L::BLOB_BYTES);
-  float sx, sw;
-  tc_scales(trailer, sx, sw);
+  unsigned char* blob2 = blob + (size_t)n_chunks * L::B1_BYTES;
+  float* wsec = reinterpret_cast<float*>(blob2 + (size_t)n_chunks * L::B2_BYTES);  // [n_chunks * NC]
+  float* s2sec = wsec + (size_t)n_chunks * L::NC;                                   // [round_up(n_chunks, 4)]
+  float* trailer = s2sec + ((n_chunks + 3) & ~3);
+  const TcScales sc = tc_scales(trailer, gamma);
   if (idx == 0) {
-    trailer[2] = sx;
-    trailer[3] = 1.f / sx;
-    trailer[4] = sw;
-    trailer[5] = 1.f / sw;
-    trailer[6] = 0.f;
-    trailer[7] = 0.f;
+    trailer[3] = sc.sa;
+    trailer[4] = sc.tc0;
+    trailer[5] = sc.tau;
+    trailer[6] = sc.inv_g;
+    trailer[7] = gamma;
+    trailer[8] = sc.valid ? 1.f : 0.f;
+    trailer[9] = 1.f / sc.tc0;
   }
   const int j = idx / L::NC, r = idx - j * L::NC;
-  unsigned char* b = blob + (size_t)j * L::BLOB_BYTES;
   float b1[L::K1], mainv[16], corrv[16];
 #pragma unroll
   for (int k = 0; k < L::K1; ++k) b1[k] = 0.f;
@@ -284,46 +314,52 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
   for (int k = 0; k < 16; ++k) mainv[k] = corrv[k] = 0.f;
   float wv = 0.f;
   if (idx < n) {
+    wv = w[idx];
+    const float gw = sc.sg * wv;  // exact (power of two)
     float ss = 0.f;
     for (int f = 0; f < F; ++f) {
-      const float sv = sx * s[(size_t)idx * F + f];  // exact (power of two)
-      const float m2 = -2.f * sv;
-      const float hi = split_hi(m2);
+      const float sv = s[(size_t)idx * F + f];
+      const float m = sc.beta * sv;  // (-2 tau c0 / Sa) s
+      const float hi = split_hi(m);
       b1[f] = hi;                        // pairs with xh
       b1[16 + f] = hi * (1.f / 256.f);   // pairs with 256 xl
-      b1[32 + f] = (m2 - hi) * 256.f;    // pairs with xh / 256
-      const float sh = split_hi(sv);
-      mainv[f] = sh;
-      corrv[f] = sv - sh;
+      b1[32 + f] = (m - hi) * 256.f;     // pairs with xh / 256
+      const float p = gw * sv;
+      const float ph = split_hi(p);
+      mainv[f] = ph;
+      corrv[f] = p - ph;
       ss = fmaf(sv, sv, ss);
     }
-    const float s1 = split_hi(ss), s2 = split_hi(ss - s1), s3 = ss - s1 - s2;
-    b1[14] = s1;  // x 1
-    b1[15] = s2;  // x 1
-    b1[30] = s3;  // x 1
-    b1[31] = 1.f;  // x xx1
-    b1[46] = 1.f;  // x xx2
-    b1[47] = 1.f;  // x xx3
-    mainv[L::ONES_ROW] = 1.f;
-    wv = sw * w[idx];
+    const float S = fmaf(sc.tc0, ss, sc.tau);  // tau (1 + c0 |s|^2)
+    const float s1 = split_hi(S), s2 = split_hi(S - s1), s3 = S - s1 - s2;
+    b1[14] = s1;   // x 1
+    b1[15] = s2;   // x 1
+    b1[30] = s3;   // x 1
+    b1[31] = 1.f;  // x X1   (X = tau c0 |x|^2, three terms)
+    b1[46] = 1.f;  // x X2
+    b1[47] = 1.f;  // x X3
+    const float gh = split_hi(gw);
+    mainv[L::ONES_ROW] = gh;
+    corrv[L::ONES_ROW] = gw - gh;
+    atomicMax(reinterpret_cast<int*>(s2sec) + j, __float_as_int(ss));
   } else {
-    b1[14] = 32768.f;  // padding rows: rho' >= 2^15 - |x'|^2, never near; weight 0 removes them from every sum
+    b1[14] = 32768.f;  // padding rows: T >= 2^15, never near; weight 0 removes them from every sum
   }
-  __half* b1p = reinterpret_cast<__half*>(b + L::OFF_B1);
+  __half* b1p = reinterpret_cast<__half*>(blob + (size_t)j * L::B1_BYTES);
 #pragma unroll
   for (int k = 0; k < L::K1; ++k) b1p[(k >> 3) * (L::NC * 8) + r * 8 + (k & 7)] = __float2half_rn(b1[k]);
   // GEMM2 image of the 8-support step ks = r / 8: K slot i = r % 8 multiplies ch of support r, slot 8 + i its cl
-  __half* b2p = reinterpret_cast<__half*>(b + L::OFF_B2 + (r >> 3) * L::B2_STEP_BYTES);
+  __half* b2p = reinterpret_cast<__half*>(blob2 + (size_t)j * L::B2_BYTES + (r >> 3) * L::B2_STEP_BYTES);
   const int i = r & 7;
 #pragma unroll
   for (int f = 0; f < 16; ++f) {
     const __half hm = __float2half_rn(mainv[f]);
-    b2p[0 * (L::N2 * 8) + f * 8 + i] = hm;                               // slot i,     row f:      sh (row 14: 1)
+    b2p[0 * (L::N2 * 8) + f * 8 + i] = hm;                               // slot i,     row f:      (Sg w s)_h (row 14: (Sg w)_h)
     b2p[1 * (L::N2 * 8) + f * 8 + i] = hm;                               // slot 8 + i, row f
-    b2p[0 * (L::N2 * 8) + (16 + f) * 8 + i] = __float2half_rn(corrv[f]);  // slot i,     row 16 + f: s - sh
+    b2p[0 * (L::N2 * 8) + (16 + f) * 8 + i] = __float2half_rn(corrv[f]);  // slot i,     row 16 + f: low parts
     b2p[1 * (L::N2 * 8) + (16 + f) * 8 + i] = __float2half_rn(0.f);
   }
-  reinterpret_cast<float*>(b + L::OFF_W)[r] = wv;
+  wsec[idx] = wv;
 }
 
 #ifdef DC_TC_ENABLE_TRACE
@@ -332,16 +368,22 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
 #else
 #define DC_TC_TRACE(slot, gidx) do { } while (0)
 #endif
-#define DC_TC_TRACE_TILE(ev) do { if (warp == 0) DC_TC_TRACE((int)(t - t0), 50 + (ev)); } while (0)
+// tile events: slot = local tile index (< 16), row 50 + ev (non-owner warp 0: ev 0..4, owner warp 4: ev 8..12)
+#define DC_TC_TRACE_TILE(w, ev) do { if (warp == (w)) DC_TC_TRACE(ti, 50 + (ev)); } while (0)
 
 // ---- the kernel -----------------------------------------------------------------------------------------------
 enum TcMode { TC_SCORE = 0, TC_GRAD = 1 };
+
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// named barriers (0 is __syncthreads)
+enum { TCB_FK = 1, TCB_EPI = 2, TCB_OWN = 3, TCB_LOW = 4, TCB_ACC = 5, TCB_END = 6 };
 
 // Exact evaluation of queued near pairs: half-warp h takes one entry, lane f of the half takes feature f (direct
 // difference against the fp32 support row), the 16 squares are summed with shuffles, and the pair's score / feature-
 // gradient terms are added to the WARP'S OWN shared-memory accumulators of that row, strictly in queue (= column)
 // order — so a row's result does not depend on its position in the batch nor on timing.  Four entries per half-warp
-// are in flight at once so the L2 latency of the support rows overlaps.
+// are in flight at once; the rows were prefetched into L1 when the pairs were queued.
 __device__ __noinline__ void tc_drain_pairs(const TcArgs& a, const uint32_t* queue, int count, const float* xs,
                                             float* gacc_w, float* sacc_w, int lane) {
   const int h = lane >> 4, f = lane & 15;
@@ -383,51 +425,70 @@ __device__ __noinline__ void tc_drain_pairs(const TcArgs& a, const uint32_t* que
       }
     }
   }
+  if (a.stats != nullptr && lane == 0) atomicAdd(a.stats, (unsigned long long)count);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __grid_constant__ TcArgs a) {
   using L = TcLayout;
-  constexpr int NC = L::NC, RS = L::RS, FM = L::FMAX, QT = L::QTHREADS;
+  constexpr int NC = L::NC, FM = L::FMAX, QT = L::QTHREADS, TM = L::TM;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::SM_BAR);
-  uint64_t* bar_full = bars;             // [RS]  TMA -> MMA / query threads
-  uint64_t* bar_free = bars + RS;        // [RS]  GEMM2 done -> TMA
-  uint64_t* bar_rho = bars + 2 * RS;     // [2]   GEMM1 done -> query threads
-  uint64_t* bar_cc = bars + 2 * RS + 2;  // [2]   query threads -> GEMM2
-  uint64_t* bar_a = bars + 2 * RS + 4;   // [1]   A operand written -> GEMM1
-  uint64_t* bar_g = bars + 2 * RS + 5;   // [1]   last GEMM2 of the tile done -> epilogue
+  uint64_t* bar_b1full = bars;        // [2]   TMA -> GEMM1
+  uint64_t* bar_b2full = bars + 2;    // [2]   TMA -> GEMM2
+  uint64_t* bar_b2free = bars + 4;    // [2]   GEMM2 done -> TMA
+  uint64_t* bar_rho = bars + 6;       // [2]   GEMM1 done -> query threads (and -> TMA: the B1 slot is free)
+  uint64_t* bar_cc = bars + 8;        // [2]   query threads -> GEMM2
+  uint64_t* bar_a = bars + 10;        // [1]   A operand written -> GEMM1
+  uint64_t* bar_g = bars + 11;        // [2]   last GEMM2 of the tile done -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::SM_TMEM_SLOT);
-  unsigned char* ring = smem + L::SM_RING;
+  unsigned char* ring1 = smem + L::SM_RING1;
+  unsigned char* ring2 = smem + L::SM_RING2;
   unsigned char* a_op = smem + L::SM_A;
-  float* qs = reinterpret_cast<float*>(smem + L::SM_QS);
-  float* os = qs;
-  float* xs = reinterpret_cast<float*>(smem + L::SM_XS);       // [128][16] features of the tile (near-pair path)
-  float* gacc = reinterpret_cast<float*>(smem + L::SM_GEX);    // [8][32][16] exact feature-gradient terms, per warp
-  float* sacc = gacc + L::QWARPS * 32 * 16;                    // [8][32] exact score terms, per warp
-  float* sc_p = reinterpret_cast<float*>(smem + L::SM_ROWS);   // [128] score partial of the second column half
-  float* thr_s = sc_p + L::TM;                                 // [128] near threshold on rho'
+  float* xs_all = reinterpret_cast<float*>(smem + L::SM_XS);     // [2][128][16]
+  float* sacc = reinterpret_cast<float*>(smem + L::SM_ACC);      // [8][32]
+  float* gacc = sacc + L::QWARPS * 32;                           // [8][32][16]
+  float* os = gacc + 4 * 32 * 16;                                // [128][n_out] over the owners' accumulators
+  float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);     // [2][128][QS_DOF]
+  float* sc_p = reinterpret_cast<float*>(smem + L::SM_ROWS);     // [128] score partial of the lower column half
+  float* xx_all = sc_p + TM;                                     // [2][128] |x|^2 (negative: out of f16 range)
   uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L::SM_QUEUE);
 
   const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
   const long long t1 = (long long)(blockIdx.x + 1) * a.n_tiles / gridDim.x;
+  const int ntile = (int)(t1 - t0);
   const int nch = a.n_chunks;
-  const uint32_t total = (uint32_t)((t1 - t0) * nch);  // < 2^31 (checked by launch_score_tc)
+#ifdef DC_TC_ENABLE_TRACE
+  if (a.trace != nullptr && tid == 0) {  // per-CTA residency record: SM id, start / end of the CTA (globaltimer, ns)
+    unsigned smid;
+    unsigned long long now;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    a.trace[2048 + blockIdx.x * 4 + 0] = smid;
+    a.trace[2048 + blockIdx.x * 4 + 1] = (long long)now;
+    a.trace[2048 + blockIdx.x * 4 + 3] = ntile;
+  }
+#endif
+  const uint32_t total = (uint32_t)ntile * (uint32_t)nch;  // < 2^31 (checked by launch_score_tc)
+  const unsigned char* blob1 = a.blob;
+  const unsigned char* blob2 = a.blob + (size_t)nch * L::B1_BYTES;
+  const float* wsec = reinterpret_cast<const float*>(blob2 + (size_t)nch * L::B2_BYTES);
+  const float* s2sec = wsec + (size_t)nch * NC;
+  const float* trailer = s2sec + ((nch + 3) & ~3);
 
   if (warp == L::CTRL_WARP) {
     if (lane == 0) {
-      for (int i = 0; i < RS; ++i) {
-        mbar_init(&bar_full[i], 1);
-        mbar_init(&bar_free[i], 1);
-      }
       for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_b1full[i], 1);
+        mbar_init(&bar_b2full[i], 1);
+        mbar_init(&bar_b2free[i], 1);
         mbar_init(&bar_rho[i], 1);
         mbar_init(&bar_cc[i], QT);
+        mbar_init(&bar_g[i], 1);
       }
-      mbar_init(bar_a, L::TM);
-      mbar_init(bar_g, 1);
+      mbar_init(bar_a, TM);
       fence_mbar_init();
     }
     __syncwarp();
@@ -439,84 +500,88 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
   const uint32_t tmem = *tmem_slot;
 
   // Register reallocation between the warpgroups (setmaxnreg): the kernel is launched with 80 registers per thread
-  // (12 warps x 2 CTAs per SM); the control warpgroup keeps 32 and the two query warpgroups grow to 104 (32 x 128 + 104 x 256 = the CTA's pool).
+  // (12 warps x 2 CTAs per SM); the service warpgroup keeps 32 and the two query warpgroups grow to 104.
   if (warp >= L::CTRL_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
-    // ================= control warp: TMA producer + MMA issuer (one elected lane issues); warps 9..11 idle =========
-    if (warp == L::CTRL_WARP && total > 0) {
+    if (warp == L::CTRL_WARP) {
+      // ================= MMA issuer: GEMM2(j) then GEMM1(j + 2), in that order, from ONE thread ======================
       constexpr uint32_t idesc1 = umma_idesc_f16(NC);
       constexpr uint32_t idesc2 = umma_idesc_f16(L::N2);
       const uint32_t a_s = smem_u32(a_op);
-      uint32_t issued = 0;
-      auto issue = [&]() {
-        const int slot = (int)(issued % RS);
-        const int chunk = (int)(issued % nch);
-        if (elect_one()) {
-          mbar_expect_tx(&bar_full[slot], L::BLOB_BYTES);
-          tma_bulk_g2s(ring + (size_t)slot * L::BLOB_BYTES, a.blob + (size_t)chunk * L::BLOB_BYTES, L::BLOB_BYTES,
-                       &bar_full[slot]);
-        }
-        __syncwarp();
-        ++issued;
-      };
-      for (int i = 0; i < RS && issued < total; ++i) issue();
-
-      auto gemm2 = [&](uint32_t g, bool first_of_tile) {
-        const int st = (int)(g & 1), slot = (int)(g % RS);
-        mbar_wait_wd(&bar_cc[st], (uint32_t)((g >> 1) & 1));
+      auto gemm1 = [&](uint32_t gg) {
+        const int st = (int)(gg & 1);
+        mbar_wait_wd(&bar_b1full[st], (uint32_t)((gg >> 1) & 1));
         tc_fence_after();
-        DC_TC_TRACE(3, g + 1);
         if (elect_one()) {
-          if constexpr (MODE == TC_GRAD) {
-            const uint32_t b_s = smem_u32(ring + (size_t)slot * L::BLOB_BYTES + L::OFF_B2);
-            const uint32_t cc = tmem + st * L::COL_STAGE;
-            const uint32_t d = tmem + L::COL_G;
+          const uint32_t b_s = smem_u32(ring1 + (size_t)st * L::B1_BYTES);
+          const uint32_t d = tmem + st * L::COL_STAGE;
 #pragma unroll
-            for (int ks = 0; ks < L::KS2; ++ks) {
-              const uint64_t bd = umma_desc(b_s + ks * L::B2_STEP_BYTES, L::N2 * 16, 128);
-              umma_f16_ts(d, cc + ks * 8, bd, idesc2, (first_of_tile && ks == 0) ? 0u : 1u);
-            }
+          for (int ks = 0; ks < L::K1 / 16; ++ks) {
+            const uint64_t ad = umma_desc(a_s + ks * 2 * (TM * 16), TM * 16, 128);
+            const uint64_t bd = umma_desc(b_s + ks * 2 * (NC * 16), NC * 16, 128);
+            umma_f16_ss(d, ad, bd, idesc1, ks == 0 ? 0u : 1u);
           }
-          umma_commit(&bar_free[slot]);
+          umma_commit(&bar_rho[st]);
         }
         __syncwarp();
       };
-
       uint32_t g = 0;
-      for (long long t = t0; t < t1; ++t) {
-        mbar_wait_wd(bar_a, (uint32_t)((t - t0) & 1));
+      for (int ti = 0; ti < ntile; ++ti) {
+        mbar_wait_wd(bar_a, (uint32_t)(ti & 1));
         tc_fence_after();
+        gemm1(g);
+        if (nch > 1) gemm1(g + 1);
         for (int j = 0; j < nch; ++j, ++g) {
-          const int st = (int)(g & 1), slot = (int)(g % RS);
-          mbar_wait_wd(&bar_full[slot], (uint32_t)((g / RS) & 1));
+          const int st = (int)(g & 1);
+          if constexpr (MODE == TC_GRAD) mbar_wait_wd(&bar_b2full[st], (uint32_t)((g >> 1) & 1));
+          mbar_wait_wd(&bar_cc[st], (uint32_t)((g >> 1) & 1));
           tc_fence_after();
-          DC_TC_TRACE(0, g);
+          DC_TC_TRACE(3, g);
           if (elect_one()) {
-            const uint32_t b_s = smem_u32(ring + (size_t)slot * L::BLOB_BYTES + L::OFF_B1);
-            const uint32_t d = tmem + st * L::COL_STAGE;
+            if constexpr (MODE == TC_GRAD) {
+              const uint32_t b_s = smem_u32(ring2 + (size_t)st * L::B2_BYTES);
+              const uint32_t cc = tmem + st * L::COL_STAGE;
+              const uint32_t d = tmem + L::COL_G + (uint32_t)(ti & 1) * L::N2;
 #pragma unroll
-            for (int ks = 0; ks < L::K1 / 16; ++ks) {
-              const uint64_t ad = umma_desc(a_s + ks * 2 * (L::TM * 16), L::TM * 16, 128);
-              const uint64_t bd = umma_desc(b_s + ks * 2 * (NC * 16), NC * 16, 128);
-              umma_f16_ss(d, ad, bd, idesc1, ks == 0 ? 0u : 1u);
+              for (int ks = 0; ks < L::KS2; ++ks) {
+                const uint64_t bd = umma_desc(b_s + ks * L::B2_STEP_BYTES, L::N2 * 16, 128);
+                umma_f16_ts(d, cc + ks * 8, bd, idesc2, (j == 0 && ks == 0) ? 0u : 1u);
+              }
             }
-            umma_commit(&bar_rho[st]);
+            umma_commit(&bar_b2free[st]);
+            if (j == nch - 1) umma_commit(&bar_g[ti & 1]);
           }
           __syncwarp();
-          DC_TC_TRACE(1, g);
-          // refill the slot of chunk g-2 as soon as its GEMM2 (issued at the end of the previous iteration) has
-          // completed: the copy of chunk g+1 then has the whole of chunk g-1's processing time to land
-          while (issued < total && g >= 2 && issued - RS <= g - 2) {
-            mbar_wait_wd(&bar_free[issued % RS], (uint32_t)(((issued / RS) + 1) & 1));
-            issue();
-          }
-          DC_TC_TRACE(2, g);
-          if (j >= 1) gemm2(g - 1, j == 1);
           DC_TC_TRACE(4, g);
+          if (j + 2 < nch) gemm1(g + 2);
+          DC_TC_TRACE(1, g);
         }
-        gemm2(g - 1, nch == 1);
-        if (elect_one()) umma_commit(bar_g);
+      }
+    } else if (warp == L::CTRL_WARP + 1) {
+      // ================= GEMM1 operand images: slot gg & 1 is free again once GEMM1(gg - 2) has completed ==============
+      for (uint32_t gg = 0; gg < total; ++gg) {
+        const int st = (int)(gg & 1);
+        if (gg >= 2) mbar_wait_wd(&bar_rho[st], (uint32_t)(((gg - 2) >> 1) & 1));
+        if (elect_one()) {
+          mbar_expect_tx(&bar_b1full[st], L::B1_BYTES);
+          tma_bulk_g2s(ring1 + (size_t)st * L::B1_BYTES, blob1 + (size_t)(gg % (uint32_t)nch) * L::B1_BYTES, L::B1_BYTES,
+                       &bar_b1full[st]);
+        }
         __syncwarp();
+      }
+    } else if (warp == L::CTRL_WARP + 2) {
+      // ================= GEMM2 operand images: slot gg & 1 is free again once GEMM2(gg - 2) has completed ==============
+      if constexpr (MODE == TC_GRAD) {
+        for (uint32_t gg = 0; gg < total; ++gg) {
+          const int st = (int)(gg & 1);
+          if (gg >= 2) mbar_wait_wd(&bar_b2free[st], (uint32_t)(((gg - 2) >> 1) & 1));
+          if (elect_one()) {
+            mbar_expect_tx(&bar_b2full[st], L::B2_BYTES);
+            tma_bulk_g2s(ring2 + (size_t)st * L::B2_BYTES, blob2 + (size_t)(gg % (uint32_t)nch) * L::B2_BYTES, L::B2_BYTES,
+                         &bar_b2full[st]);
+          }
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -524,8 +589,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
     // ================= query threads: row = 32 (warp & 3) + lane, column half = warp >> 2 ==========================
     const int row = ((warp & 3) << 5) | lane;
     const int hcol = warp >> 2;
-    // owners run FK, the A operand and the epilogue of their row: the higher-numbered half, which the warp scheduler
-    // favours — those phases are the CTA's critical path (the other half waits at the barriers)
+    // owners (upper half) run the epilogue of their row; the lower half runs FK + the A operand of the NEXT tile meanwhile
     const bool owner = hcol == 1;
     const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t* queue = queues + warp * L::QCAP;
@@ -535,134 +599,170 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
     const int n_out = 1 + (MODE == TC_GRAD ? a.n_in : 0);
     const bool fused = (MODE == TC_GRAD) ? (a.score_ld == a.grad_ld && a.score_ld == n_out && a.grad == a.score + 1)
                                          : (a.score_ld == 1);
-    const float* trailer = reinterpret_cast<const float*>(a.blob + (size_t)nch * L::BLOB_BYTES);
-    const float s2max = trailer[0], sx = trailer[2], inv_sx = trailer[3], inv_sw = trailer[5];
-    const float c0s = a.rc.c0 * inv_sx * inv_sx;  // t = 1 + c0 rho = 1 + c0s rho'   (rho' = Sx^2 rho from GEMM1)
-    uint32_t g = 0;
-    for (long long t = t0; t < t1; ++t) {
-      const long long b_base = t * L::TM;
-      const int nq = (int)min((long long)L::TM, a.batch - b_base);
-      // ---- stage the tile's configurations (coalesced), FK, A operand ----------------------------------------
-      DC_TC_TRACE_TILE(0);
-      {
-        const float* src = a.q + (size_t)b_base * a.n_in;
-        const int n_words = nq * a.n_in;
+    const bool has_fk = a.fk.type != DC_FK_NONE;
+    const float s2max = trailer[0], sa = trailer[3], tc0 = trailer[4], tau = trailer[5], inv_g = trailer[6];
+#ifdef DC_TC_ENABLE_TRACE
+    const float inv_tc0 = trailer[9];
+#endif
+    const float kq = -a.rc.grad_scale * 0.5f * a.err_coef / a.tol_pair;  // gamma err / tol
+    const float4* wrow4 = reinterpret_cast<const float4*>(wsec + hcol * (NC / 2));
+
+    // ---- lower half: configurations of tile ti -> FK -> features, |x|^2, A operand -----------------------------------
+    auto fk_stage = [&](int ti) {
+      const int buf = ti & 1;
+      const long long b_base = (t0 + ti) * TM;
+      const int nq = (int)min((long long)TM, a.batch - b_base);
+      float* xs = xs_all + buf * TM * 16;
+      float* qs = qs_all + buf * TM * L::QS_DOF;
+      const float* src = a.q + (size_t)b_base * a.n_in;
+      const int n_words = nq * a.n_in;
+      float x[FM];
+      float qv[DC_MAX_DOF];
+      if (has_fk) {
+        // coalesced staging of the tile's configurations (also what makes zero-copy reads of pinned host memory efficient)
         if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
           const float4* s4 = reinterpret_cast<const float4*>(src);
-          for (int i = tid; i < n_words / 4; i += QT) reinterpret_cast<float4*>(qs)[i] = s4[i];
+          for (int i = tid; i < n_words / 4; i += TM) reinterpret_cast<float4*>(qs)[i] = s4[i];
         } else {
-          for (int i = tid; i < n_words; i += QT) qs[i] = src[i];
+          for (int i = tid; i < n_words; i += TM) qs[i] = src[i];
         }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      float qv[DC_MAX_DOF];
-      if (owner) {
+        named_sync(TCB_LOW, TM);
 #pragma unroll
         for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (row < nq && i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
+        float xl[DC_MAX_DOF];
+#pragma unroll
+        for (int i = 0; i < DC_MAX_DOF; ++i) xl[i] = 0.f;
+        if (row < nq) fk_forward<float>(a.fk, qv, xl, 1);
+#pragma unroll
+        for (int f = 0; f < FM; ++f) x[f] = (f < F) ? xl[f] : 0.f;
+      } else {
+        // transform=None: the rows ARE the features; staged straight into the feature layout [128][16]
+        for (int i = tid; i < TM * 16; i += TM) xs[i] = 0.f;
+        named_sync(TCB_LOW, TM);
+        for (int i = tid; i < n_words; i += TM) {
+          const int r = i / a.n_in;
+          xs[r * 16 + (i - r * a.n_in)] = src[i];
+        }
+        named_sync(TCB_LOW, TM);
+#pragma unroll
+        for (int f = 0; f < FM; ++f) x[f] = xs[row * 16 + f];
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the staged configurations are consumed: the region becomes the
-      {                                                 // exact accumulators of this tile
+      float xx = 0.f, xamax = 0.f;
+#pragma unroll
+      for (int f = 0; f < FM; ++f) {
+        xx = fmaf(x[f], x[f], xx);
+        xamax = fmaxf(xamax, fabsf(x[f]));
+      }
+      {
+        float4* xr = reinterpret_cast<float4*>(xs + row * 16);
+        xr[0] = make_float4(x[0], x[1], x[2], x[3]);
+        xr[1] = make_float4(x[4], x[5], x[6], x[7]);
+        xr[2] = make_float4(x[8], x[9], x[10], x[11]);
+        xr[3] = make_float4(x[12], x[13], 0.f, 0.f);
+      }
+      // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
+      const bool in_range = (sa * xamax < 32768.f) && (tc0 * xx < 32768.f);
+      {
+        float v[L::K1];
+        const float XX = in_range ? tc0 * xx : 0.f;
+#pragma unroll
+        for (int k = 0; k < L::K1; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int f = 0; f < FM; ++f) {
+          const float xsc = in_range ? sa * x[f] : 0.f;
+          const float hi = split_hi(xsc);
+          v[f] = hi;                       // x beta s_h
+          v[16 + f] = (xsc - hi) * 256.f;  // x beta s_h / 256
+          v[32 + f] = hi * (1.f / 256.f);  // x 256 (beta s)_lo
+        }
+        const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
+        v[14] = 1.f;  // x S1   (S = tau (1 + c0 |s|^2), three terms)
+        v[15] = 1.f;  // x S2
+        v[30] = 1.f;  // x S3
+        v[31] = x1;   // x 1
+        v[46] = x2;   // x 1
+        v[47] = x3;   // x 1
+#pragma unroll
+        for (int kc = 0; kc < L::K1 / 8; ++kc) {
+          uint4 pk;
+          pk.x = pack_f16x2(v[8 * kc + 0], v[8 * kc + 1]);
+          pk.y = pack_f16x2(v[8 * kc + 2], v[8 * kc + 3]);
+          pk.z = pack_f16x2(v[8 * kc + 4], v[8 * kc + 5]);
+          pk.w = pack_f16x2(v[8 * kc + 6], v[8 * kc + 7]);
+          reinterpret_cast<uint4*>(a_op)[kc * TM + row] = pk;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_a);
+      xx_all[buf * TM + row] = in_range ? xx : -1.f;
+#ifdef DC_TC_ENABLE_TRACE
+      if (a.dbg != nullptr && t0 + ti == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a.dbg[(size_t)TM * (nch * NC) + TM * 32 + row * 16 + c] = c < FM ? x[c] : 0.f;
+      }
+#endif
+      named_arrive(TCB_FK, QT);  // features, |x|^2 (and the staged configurations) of tile ti are visible to the owners
+    };
+
+    if (!owner && ntile > 0) fk_stage(0);
+
+    uint32_t g = 0;
+    for (int ti = 0; ti < ntile; ++ti) {
+      const int buf = ti & 1;
+      const long long b_base = (t0 + ti) * TM;
+      const int nq = (int)min((long long)TM, a.batch - b_base);
+      const float* xs = xs_all + buf * TM * 16;
+      if (owner) {
+        named_sync(TCB_FK, QT);
+      } else if (ti > 0) {
+        named_sync(TCB_ACC, QT);  // the owners have read the lower half's exact accumulators of tile ti - 1
+      }
+      DC_TC_TRACE_TILE(0, 0);
+      DC_TC_TRACE_TILE(4, 8);
+      {
         float4* z = reinterpret_cast<float4*>(gacc_w + lane * 16);
         z[0] = z[1] = z[2] = z[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         sacc_w[lane] = 0.f;
       }
-      if (owner) {
-        float x[FM];
-        {
-          float xl[DC_MAX_DOF];
-#pragma unroll
-          for (int i = 0; i < DC_MAX_DOF; ++i) xl[i] = 0.f;
-          if (row < nq) fk_forward<float>(a.fk, qv, xl, 1);
-#pragma unroll
-          for (int f = 0; f < FM; ++f) x[f] = (f < F) ? xl[f] : 0.f;
-        }
-        float xx = 0.f, xamax = 0.f;
-#pragma unroll
-        for (int f = 0; f < FM; ++f) {
-          xx = fmaf(x[f], x[f], xx);
-          xamax = fmaxf(xamax, fabsf(x[f]));
-        }
-        {
-          float4* xr = reinterpret_cast<float4*>(xs + row * 16);
-          xr[0] = make_float4(x[0], x[1], x[2], x[3]);
-          xr[1] = make_float4(x[4], x[5], x[6], x[7]);
-          xr[2] = make_float4(x[8], x[9], x[10], x[11]);
-          xr[3] = make_float4(x[12], x[13], 0.f, 0.f);
-        }
-        // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
-        const bool in_range = (sx * xamax < 16384.f) && (sx * sx * xx < 32768.f);
-        {
-          float v[L::K1];
-          const float XX = in_range ? sx * sx * xx : 0.f;
-#pragma unroll
-          for (int k = 0; k < L::K1; ++k) v[k] = 0.f;
-#pragma unroll
-          for (int f = 0; f < FM; ++f) {
-            const float xsc = in_range ? sx * x[f] : 0.f;
-            const float hi = split_hi(xsc);
-            v[f] = hi;                       // x (-2 sh)
-            v[16 + f] = (xsc - hi) * 256.f;  // x (-2 sh) / 256
-            v[32 + f] = hi * (1.f / 256.f);  // x 256 (-2 s)_lo
-          }
-          const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
-          v[14] = 1.f;  // x s1
-          v[15] = 1.f;  // x s2
-          v[30] = 1.f;  // x s3
-          v[31] = x1;   // x 1
-          v[46] = x2;   // x 1
-          v[47] = x3;   // x 1
-#pragma unroll
-          for (int kc = 0; kc < L::K1 / 8; ++kc) {
-            uint4 pk;
-            pk.x = pack_f16x2(v[8 * kc + 0], v[8 * kc + 1]);
-            pk.y = pack_f16x2(v[8 * kc + 2], v[8 * kc + 3]);
-            pk.z = pack_f16x2(v[8 * kc + 4], v[8 * kc + 5]);
-            pk.w = pack_f16x2(v[8 * kc + 6], v[8 * kc + 7]);
-            reinterpret_cast<uint4*>(a_op)[kc * L::TM + row] = pk;
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(bar_a);
-        // near-pair threshold of this query, on rho' (file header): rho' below it is recomputed exactly
-        const float drho = a.err_coef * (xx + s2max);
-        const float tcrit = cbrtf(fmaxf(-a.rc.grad_scale * 0.5f * drho / a.tol_pair, 1.f));  // (gamma drho / tol)^(1/3)
-        thr_s[row] = in_range ? sx * sx * (tcrit - 1.f) / a.rc.c0 : 3.0e38f;
+      __syncwarp();
+      const float xxq = xx_all[buf * TM + row];
+      float thr_c0, thr_c1;
+      {
+        const float base = fmaxf(kq * (fmaxf(xxq, 0.f) + s2max), 1.f);
+        const float cr = cbrtf(base);
+        thr_c1 = tau * 1.001f * kq / (3.f * cr * cr);
+        thr_c0 = (xxq >= 0.f) ? tau * 1.001f * cr - thr_c1 * s2max : 3.0e38f;  // out-of-range rows: every pair is "near"
       }
-      DC_TC_TRACE_TILE(1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // xs, thr_s visible; qs free for the output records
-      DC_TC_TRACE_TILE(2);
-      const float thr = thr_s[row];
 
       P2 sc2(0.f, 0.f);
       int qcount = 0;
       for (int j = 0; j < nch; ++j, ++g) {
-        const int st = (int)(g & 1), slot = (int)(g % RS);
-        const float* wsm = reinterpret_cast<const float*>(ring + (size_t)slot * L::BLOB_BYTES + L::OFF_W) + hcol * (NC / 2);
+        const int st = (int)(g & 1);
+        const float4* wv4 = wrow4 + j * (NC / 4);  // this chunk's weights, warp-uniform 16-byte loads (L1)
         if (warp == 0) DC_TC_TRACE(8, g);
-        mbar_wait_wd(&bar_full[slot], (uint32_t)((g / RS) & 1));
-        if (warp == 0) DC_TC_TRACE(9, g);
+        const float s2j = __ldg(s2sec + j);
         mbar_wait_wd(&bar_rho[st], (uint32_t)((g >> 1) & 1));
         tc_fence_after();
         if (warp == 0) DC_TC_TRACE(10, g);
         const uint32_t tcol = tm_lane + st * L::COL_STAGE + hcol * (NC / 2);
-        uint32_t r[NC / 2];
-        tmem_ld16(tcol, r);
-        tmem_ld16(tcol + 16, r + 16);
-        tmem_ld16(tcol + 32, r + 32);
-#pragma unroll
-        for (int bt = 0; bt < 3; ++bt) {
-          if (bt == 0) {
-            tmem_wait_ld();
-            if (warp == 0) DC_TC_TRACE(11, g);
-          }
-          uint32_t* rb = r + bt * 16;
+        // two register buffers of 16 columns: the load of batch b + 1 is in flight while batch b is processed
+        uint32_t ra[16], rc[16];
+        tmem_ld16(tcol, ra);
+        tmem_ld16(tcol + 16, rc);
+        // near threshold of this (query, chunk) on T: pairs with 1 + c0 rho < (gamma drho / tol)^(1/3), drho = err (|x|^2 +
+        // max_chunk |s|^2), are recomputed exactly.  The cube root is bounded from above by its tangent at the largest chunk
+        // maximum (concave function): one FFMA per chunk, exact for the widest chunk, conservative for the others.
+        const float thr = fmaf(thr_c1, s2j, thr_c0);
+        auto batch = [&](uint32_t* rb, const int bt) {
           const int col0 = bt * 16;
-          if (a.dbg != nullptr && t == 0) {
+#ifdef DC_TC_ENABLE_TRACE
+          if (a.dbg != nullptr && t0 + ti == 0) {
 #pragma unroll
             for (int c = 0; c < 16; ++c)
-              a.dbg[(size_t)row * (nch * NC) + j * NC + hcol * (NC / 2) + col0 + c] = __uint_as_float(rb[c]) * inv_sx * inv_sx;
+              a.dbg[(size_t)row * (nch * NC) + j * NC + hcol * (NC / 2) + col0 + c] = (__uint_as_float(rb[c]) - tau) * inv_tc0;
           }
-          // ---- near pairs: queued for exact evaluation, removed from the tensor-core sums (rho' := huge -> u = 0) ----
+#endif
+          // ---- near pairs: queued for exact evaluation, removed from the tensor-core sums (T := huge -> u = 0) ----
           float mn = fminf(__uint_as_float(rb[0]), __uint_as_float(rb[1]));
 #pragma unroll
           for (int c = 2; c < 16; c += 2) mn = fminf(mn, fminf(__uint_as_float(rb[c]), __uint_as_float(rb[c + 1])));
@@ -683,7 +783,11 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
               if (n0 + c >= a.n_sv) break;  // padding columns (only reachable for out-of-range queries): zero weight
               const bool near = (nearmask >> c) & 1u;
               const uint32_t bal = __ballot_sync(0xffffffffu, near);
-              if (near) queue[qcount + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)row << 24) | (uint32_t)(n0 + c);
+              if (near) {
+                queue[qcount + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)row << 24) | (uint32_t)(n0 + c);
+              }
+              if (lane == 0)  // the row is read when the queue is drained: start pulling it into L1 now
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.table + (size_t)(n0 + c) * a.row_stride));
               qcount += __popc(bal);
               if (qcount > L::QCAP - 32) {
                 __syncwarp();
@@ -693,113 +797,135 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
               }
             }
           }
-          // ---- all pairs: radial profile on the tensor-core rho', packed over column pairs ---------------------
+          // ---- all pairs: radial profile on the tensor-core T, packed over column pairs ------------------------
           uint32_t outp[16];  // per 8 supports: 4 x f16x2 ch, 4 x f16x2 cl  (GEMM2 K slots 0..7, 8..15)
+          float4 w4[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) w4[c] = __ldg(wv4 + bt * 4 + c);
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
-            const float2 w2 = *reinterpret_cast<const float2*>(wsm + col0 + c);
-            const P2 rho2(__uint_as_float(rb[c]), __uint_as_float(rb[c + 1]));
-            const P2 tt = pfma_bb(rho2, c0s, 1.0f);
-            const float rr = fast_rcp(tt.lo() * tt.hi());  // one MUFU per column pair: 1/t0 = t1 / (t0 t1)
-            const P2 u = pmul_b(P2(tt.hi(), tt.lo()), rr);
-            const P2 k = pmul(u, u);
-            const P2 wk = pmul(P2(w2), k);
-            sc2 = padd(sc2, wk);
+            const float2 w2 = (c & 2) ? make_float2(w4[c >> 2].z, w4[c >> 2].w) : make_float2(w4[c >> 2].x, w4[c >> 2].y);
+            const float ta = __uint_as_float(rb[c]), tb = __uint_as_float(rb[c + 1]);
+            const float rr = fast_rcp(ta * tb);  // one MUFU per column pair: 1/ta = tb / (ta tb)
+            const P2 u = pmul_b(P2(tb, ta), rr);  // 32 u
+            const P2 k = pmul(u, u);              // 2^10 u^2
+            sc2 = pfma(P2(w2), k, sc2);
             if constexpr (MODE == TC_GRAD) {
-              const P2 cc = pmul(wk, u);
-              const P2 ch(split_hi(cc.lo()), split_hi(cc.hi()));
-              const P2 cl = padd(cc, P2(-ch.lo(), -ch.hi()));
+              // cc = 2^15 u^3 split into two 11-bit f16 terms WITHOUT the conversion unit (F2FP shares the XU pipe with
+              // MUFU and was the kernel's binding pipe, profiles/r02e_*): scaling by 2^-112 re-biases the fp32 exponent
+              // to f16's, after which `bits >> 13` IS the f16 bit pattern (truncated; f16 denormals included).
+              const P2 cc = pmul_b(pmul(k, u), 0x1p-112f);
+              const uint32_t b0 = __float_as_uint(cc.lo()) & 0xffffe000u, b1 = __float_as_uint(cc.hi()) & 0xffffe000u;
+              const P2 cl = padd(cc, P2(-__uint_as_float(b0), -__uint_as_float(b1)));  // exact
               const int o = (c >> 3) * 8 + ((c & 7) >> 1);
-              outp[o] = pack_f16x2(ch.lo(), ch.hi());
-              outp[o + 4] = pack_f16x2(cl.lo(), cl.hi());
+              outp[o] = b1 * 8u + (b0 >> 13);  // {ch(c + 1) : ch(c)} as f16x2 (the low 13 bits of b1 are zero)
+              outp[o + 4] = __byte_perm(__float_as_uint(cl.lo()) << 3, __float_as_uint(cl.hi()) << 3, 0x7632);
             }
           }
           if constexpr (MODE == TC_GRAD) tmem_st16(tcol + col0, outp);
-        }
+        };
+        tmem_wait_ld();
+        if (warp == 0) DC_TC_TRACE(11, g);
+        batch(ra, 0);
+        tmem_ld16(tcol + 32, ra);  // batch 2 into the first buffer (its values are consumed)
+        batch(rc, 1);
+        tmem_wait_ld();
+        batch(ra, 2);
         if (warp == 0) DC_TC_TRACE(12, g);
         if constexpr (MODE == TC_GRAD) tmem_wait_st();
         tc_fence_before();
         if (warp == 0) DC_TC_TRACE(13, g);
         mbar_arrive(&bar_cc[st]);
       }
-      DC_TC_TRACE_TILE(3);
+      DC_TC_TRACE_TILE(0, 1);
+      DC_TC_TRACE_TILE(4, 9);
       if (qcount > 0) {
         __syncwarp();
         tc_drain_pairs(a, queue, qcount, xs, gacc_w, sacc_w, lane);
       }
-      DC_TC_TRACE_TILE(4);
-      if (!owner) sc_p[row] = sc2.lo() + sc2.hi();
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // exact terms and second-half partial scores are complete
-      DC_TC_TRACE_TILE(5);
+      DC_TC_TRACE_TILE(0, 2);
+      DC_TC_TRACE_TILE(4, 10);
 
-      // ---- epilogue (row owners): G from TMEM, feature gradient, J_FK^T, records into shared memory -----------------
-      if (owner) {
-        float gx[DC_MAX_DOF], xl[DC_MAX_DOF];
-#pragma unroll
-        for (int i = 0; i < DC_MAX_DOF; ++i) {
-          gx[i] = 0.f;
-          xl[i] = xs[row * 16 + i];
-        }
-        mbar_wait_wd(bar_g, (uint32_t)((t - t0) & 1));
-        tc_fence_after();
-        if constexpr (MODE == TC_GRAD) {
-          uint32_t gm[16], gc[16];
-          tmem_ld16(tm_lane + L::COL_G, gm);
-          tmem_ld16(tm_lane + L::COL_G + 16, gc);
-          tmem_wait_ld();
-          if (a.dbg != nullptr && t == 0) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              a.dbg[(size_t)L::TM * (nch * NC) + row * 32 + c] = __uint_as_float(gm[c]);
-              a.dbg[(size_t)L::TM * (nch * NC) + row * 32 + 16 + c] = __uint_as_float(gc[c]);
-              a.dbg[(size_t)L::TM * (nch * NC) + L::TM * 32 + row * 16 + c] = xl[c];
-            }
-          }
-          const float csum = __uint_as_float(gm[L::ONES_ROW]);
-#pragma unroll
-          for (int f = 0; f < FM; ++f) {
-            const float gsum = (__uint_as_float(gm[f]) + __uint_as_float(gc[f])) * inv_sx;  // sum cc' s
-            const float gex = gacc_w[lane * 16 + f - 4 * 32 * 16] + gacc_w[lane * 16 + f];  // column halves 0 + 1
-            gx[f] = a.rc.grad_scale * (fmaf(xl[f], csum, -gsum) * inv_sw + gex);
-          }
-        }
-        tc_fence_before();
-        const float score =
-            a.rc.score_scale * ((sc_p[row] + (sc2.lo() + sc2.hi())) * inv_sw + (sacc_w[lane - 4 * 32] + sacc_w[lane]));
-        asm volatile("bar.sync 2, 128;" ::: "memory");  // every owner has read its accumulators: the region becomes `os`
-        if (row < nq) {
-          float* rec = os + row * n_out;
-          rec[0] = score;
-          if constexpr (MODE == TC_GRAD) {
-            const float scale = (a.grad_out != nullptr) ? a.grad_out[b_base + row] : 1.f;
-            if (a.fk.type == DC_FK_NONE) {
-              for (int f = 0; f < F; ++f) rec[1 + f] = scale * gx[f];
-            } else {
-              float gq[DC_MAX_DOF];
-#pragma unroll
-              for (int i = 0; i < DC_MAX_DOF; ++i) gq[i] = 0.f;
-              fk_vjp<float>(a.fk, qv, xl, 1, gx, 1, gq);
-              for (int i = 0; i < a.n_in; ++i) rec[1 + i] = scale * gq[i];
-            }
-          }
-        }
-      } else {
-        // the accumulator must not be overwritten by the next tile's first GEMM2 before the owners have read it: the
-        // owners' wait on bar_g above orders that (their next arrival on bar_cc comes after this epilogue)
+      if (!owner) {
+        sc_p[row] = sc2.lo() + sc2.hi();
+        __threadfence_block();
+        named_arrive(TCB_EPI, QT);  // lower half's partial scores and exact terms of tile ti are complete
+        if (ti + 1 < ntile) fk_stage(ti + 1);
+        DC_TC_TRACE_TILE(0, 3);
+        continue;
       }
-      DC_TC_TRACE_TILE(6);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      DC_TC_TRACE_TILE(7);
+
+      // ---- epilogue (owners): G from TMEM, feature gradient, J_FK^T, records into shared memory ------------------------
+      named_sync(TCB_EPI, QT);
+      float gx[DC_MAX_DOF], xl[DC_MAX_DOF];
+#pragma unroll
+      for (int i = 0; i < DC_MAX_DOF; ++i) {
+        gx[i] = 0.f;
+        xl[i] = xs[row * 16 + i];
+      }
+      mbar_wait_wd(&bar_g[ti & 1], (uint32_t)((ti >> 1) & 1));
+      tc_fence_after();
+      DC_TC_TRACE_TILE(4, 11);
+      if constexpr (MODE == TC_GRAD) {
+        uint32_t gm[16], gc[16];
+        tmem_ld16(tm_lane + L::COL_G + (uint32_t)(ti & 1) * L::N2, gm);
+        tmem_ld16(tm_lane + L::COL_G + (uint32_t)(ti & 1) * L::N2 + 16, gc);
+        tmem_wait_ld();
+#ifdef DC_TC_ENABLE_TRACE
+        if (a.dbg != nullptr && t0 + ti == 0) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            a.dbg[(size_t)TM * (nch * NC) + row * 32 + c] = __uint_as_float(gm[c]);
+            a.dbg[(size_t)TM * (nch * NC) + row * 32 + 16 + c] = __uint_as_float(gc[c]);
+          }
+        }
+#endif
+        const float csum = __uint_as_float(gm[L::ONES_ROW]) + __uint_as_float(gc[L::ONES_ROW]);  // sum cc w
+#pragma unroll
+        for (int f = 0; f < FM; ++f) {
+          const float gsum = __uint_as_float(gm[f]) + __uint_as_float(gc[f]);              // sum cc w s
+          const float gex = gacc_w[lane * 16 + f - 4 * 32 * 16] + gacc_w[lane * 16 + f];  // column halves 0 + 1
+          gx[f] = a.rc.grad_scale * (fmaf(xl[f], csum, -gsum) * inv_g + gex);
+        }
+      }
+      tc_fence_before();
+      const float score = a.rc.score_scale * ((sc_p[row] + (sc2.lo() + sc2.hi())) * (1.f / 1024.f) +
+                                              (sacc_w[lane - 4 * 32] + sacc_w[lane]));
+      if (ti + 1 < ntile) named_arrive(TCB_ACC, QT);  // the lower half may reset its accumulators for tile ti + 1
+      named_sync(TCB_OWN, TM);  // every owner has read its accumulators: their region becomes `os`
+      if (row < nq) {
+        float* rec = os + row * n_out;
+        rec[0] = score;
+        if constexpr (MODE == TC_GRAD) {
+          const float scale = (a.grad_out != nullptr) ? a.grad_out[b_base + row] : 1.f;
+          if (!has_fk) {
+            for (int f = 0; f < F; ++f) rec[1 + f] = scale * gx[f];
+          } else {
+            float gq[DC_MAX_DOF], qv[DC_MAX_DOF];
+            const float* qs = qs_all + buf * TM * L::QS_DOF;
+#pragma unroll
+            for (int i = 0; i < DC_MAX_DOF; ++i) {
+              gq[i] = 0.f;
+              qv[i] = (i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
+            }
+            fk_vjp<float>(a.fk, qv, xl, 1, gx, 1, gq);
+            for (int i = 0; i < a.n_in; ++i) rec[1 + i] = scale * gq[i];
+          }
+        }
+      }
+      DC_TC_TRACE_TILE(4, 12);
+      named_sync(TCB_OWN, TM);
+      const int otid = tid - TM;  // 0 .. 127
       if (fused) {
         // n_bcast > 0: the same block goes to every rank's gathered buffer (peer stores over NVLink) — the all-gather of
         // the multi-GPU path, overlapped with the other tiles' arithmetic
         const int n_dst = a.n_bcast > 0 ? a.n_bcast : 1;
         const size_t off = (size_t)(a.score - (a.n_bcast > 0 ? a.bcast[0] : a.score)) + (size_t)b_base * n_out;
         const int n_words = nq * n_out;
-        if (a.n_bcast > 0 && (n_words & 3) == 0) {
+        if (a.n_bcast > 0 && (n_words & 3) == 0 && (off & 3) == 0) {
           // one bulk TMA store of the whole block per destination (shared -> peer global, large NVLink packets, no
-          // thread is held by the transfer); the block is released below once the copies have read it
-          if (tid == 0) {
+          // thread is held by the transfer); the bases are 16-byte aligned (dc_score_grad_bcast), so `off & 3` decides
+          if (otid == 0) {
             fence_proxy_async();
             for (int k = 0; k < n_dst; ++k)
               asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.bcast[k] + off),
@@ -812,50 +938,65 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
           for (int k = 0; k < n_dst; ++k) {
             float* dst = (a.n_bcast > 0 ? a.bcast[k] : a.score) + off;
             if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-              for (int i = tid; i < n_words / 4; i += QT) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
+              for (int i = otid; i < n_words / 4; i += TM) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
             } else {
-              for (int i = tid; i < n_words; i += QT) dst[i] = os[i];
+              for (int i = otid; i < n_words; i += TM) dst[i] = os[i];
             }
           }
         }
       } else {
-        if (tid < nq) a.score[(size_t)(b_base + tid) * a.score_ld] = os[tid * n_out];
+        if (otid < nq) a.score[(size_t)(b_base + otid) * a.score_ld] = os[otid * n_out];
         if constexpr (MODE == TC_GRAD) {
-          for (int i = tid; i < nq * a.n_in; i += QT) {
+          for (int i = otid; i < nq * a.n_in; i += TM) {
             const int tq = i / a.n_in, c = i - tq * a.n_in;
             a.grad[(size_t)(b_base + tq) * a.grad_ld + c] = os[tq * n_out + 1 + c];
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // qs / os are rewritten by the next tile
-      DC_TC_TRACE_TILE(8);
+      named_sync(TCB_OWN, TM);  // `os` is consumed: the owners' accumulators are reset by the next tile
+      DC_TC_TRACE_TILE(4, 13);
     }
+    if (tid == TM && a.n_bcast > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // peer stores performed
   }
 
-  if (tid == 0 && a.n_bcast > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // peer stores performed
-  tc_fence_before();
-  __syncthreads();
-  if (warp == L::CTRL_WARP) {
-    tc_fence_after();
-    tmem_dealloc(tmem, L::TMEM_COLS);
+  // teardown: the MMA issuer (owner of the TMEM allocation) waits for the query warps; the TMA warps just leave
+  if (warp <= L::CTRL_WARP) {
+    tc_fence_before();
+    named_sync(TCB_END, QT + 32);
+#ifdef DC_TC_ENABLE_TRACE
+    if (a.trace != nullptr && tid == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      a.trace[2048 + blockIdx.x * 4 + 2] = (long long)now;
+    }
+#endif
+    if (warp == L::CTRL_WARP) {
+      tc_fence_after();
+      tmem_dealloc(tmem, L::TMEM_COLS);
+    }
   }
 }
 
 inline int tc_n_chunks(long long n_sv) { return (int)((n_sv + TcLayout::NC - 1) / TcLayout::NC); }
-inline size_t tc_blob_bytes(long long n_sv) {
-  return (size_t)tc_n_chunks(n_sv) * TcLayout::BLOB_BYTES + TcLayout::TRAILER_FLOATS * 4;
+inline size_t tc_trailer_offset(long long n_sv) {
+  const size_t nch = (size_t)tc_n_chunks(n_sv);
+  return nch * (TcLayout::B1_BYTES + TcLayout::B2_BYTES) + (nch * TcLayout::NC + ((nch + 3) & ~(size_t)3)) * 4;
+}
+inline size_t tc_blob_bytes(long long n_sv) { return tc_trailer_offset(n_sv) + TcLayout::TRAILER_FLOATS * 4; }
+inline const float* tc_trailer(const void* blob, long long n_sv) {
+  return reinterpret_cast<const float*>(static_cast<const unsigned char*>(blob) + tc_trailer_offset(n_sv));
 }
 
-// Packs S_feat[N,F], w[N] into `blob` (tc_blob_bytes(N) bytes, 128-byte aligned).  Three launches on `stream`.
-inline int launch_pack_supports_tc(const float* s_feat, const float* w, long long n, int F, unsigned char* blob,
+// Packs S_feat[N,F], w[N] for RQKernel(gamma, p = 2) into `blob` (tc_blob_bytes(N) bytes, 128-byte aligned).
+inline int launch_pack_supports_tc(const float* s_feat, const float* w, long long n, int F, float gamma, unsigned char* blob,
                                    cudaStream_t stream) {
   using L = TcLayout;
   const int nch = tc_n_chunks(n);
-  int* trailer = reinterpret_cast<int*>(blob + (size_t)nch * L::BLOB_BYTES);
-  DC_CUDA_OK(cudaMemsetAsync(trailer, 0, L::TRAILER_FLOATS * 4, stream));
+  DC_CUDA_OK(cudaMemsetAsync(blob, 0, tc_blob_bytes(n), stream));
+  int* trailer = reinterpret_cast<int*>(const_cast<float*>(tc_trailer(blob, n)));
   tc_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(s_feat, w, (int)n, F, trailer);
   DC_LAUNCH_CHECK();
-  pack_supports_tc_kernel<<<(unsigned)((nch * L::NC + 127) / 128), 128, 0, stream>>>(s_feat, w, (int)n, F, nch, blob);
+  pack_supports_tc_kernel<<<(unsigned)((nch * L::NC + 127) / 128), 128, 0, stream>>>(s_feat, w, (int)n, F, nch, gamma, blob);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
@@ -867,8 +1008,19 @@ int launch_score_tc(TcArgs& a, int num_sms, cudaStream_t stream) {
   a.n_chunks = tc_n_chunks(a.n_sv);
   const int grid = (int)min((long long)2 * num_sms, (long long)a.n_tiles);
   if (((long long)a.n_tiles / grid + 1) * a.n_chunks >= (1LL << 31) || a.n_sv >= (1 << 24)) return DC_ERR_UNSUPPORTED;
+  if (a.fk.type != DC_FK_NONE && a.n_in > L::QS_DOF) return DC_ERR_UNSUPPORTED;
   auto kern = score_tc_kernel<MODE>;
-  DC_SET_FUNC_ATTR_ONCE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SM_BYTES);
+  {
+    static PerDeviceOnce once;
+    int dev = 0;
+    const int p = once.pending(&dev);
+    if (p < 0) return DC_ERR_NO_DEVICE;
+    if (p > 0) {
+      DC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SM_BYTES));
+      DC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      once.mark(dev);
+    }
+  }
   kern<<<grid, L::THREADS, L::SM_BYTES, stream>>>(a);
   DC_LAUNCH_CHECK();
   return DC_OK;

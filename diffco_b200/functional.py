@@ -56,7 +56,8 @@ class SupportSet:
     configuration in BASELINE.json) and is re-read by every launch from L2.
     """
 
-    def __init__(self, s_feat: torch.Tensor, weights: torch.Tensor, device: Optional[torch.device] = None):
+    def __init__(self, s_feat: torch.Tensor, weights: torch.Tensor, device: Optional[torch.device] = None,
+                 kernel: Optional[KernelDesc] = None):
         device = device or _require_cuda()
         lib = _lib.load()
         s = s_feat.detach().reshape(s_feat.shape[0], -1)
@@ -80,20 +81,26 @@ class SupportSet:
                                             self.table.data_ptr(), _stream_ptr(device)), "dc_pack_supports")
         self.dtype = dtype
         self.device = device
-        # Optional tensor-core operand image (fp32, one class, F <= 14): lets dc_score_grad run DiffCo.score with
-        # RQKernel(p = 2) on tcgen05 tensor cores (csrc/dc_score_tc.cuh).  max|s|^2 is read back once here (pack time).
+        # Optional tensor-core operand image (fp32, one class, F <= 14, RQKernel with p = 2; csrc/dc_score_tc.cuh): the
+        # kernel width and the weights are folded into the operands, so it is built for the kernel this support set is
+        # scored with.  max|s|^2 and the range check are read back once here (pack time).
         self.tc_blob = None
-        tc_ptr, s2max = None, 0.0
+        tc_ptr, s2max, tc_gamma = None, 0.0, 0.0
         nbytes = C.c_int64()
-        if lib.dc_supports_tc_bytes(self.n, self.n_features, self.n_class, code, C.byref(nbytes)) == 0:
-            self.tc_blob = torch.empty(nbytes.value + 128, dtype=torch.uint8, device=device)
-            tc_ptr = (self.tc_blob.data_ptr() + 127) // 128 * 128
+        if (kernel is not None and kernel.kind == _lib.DC_K_RQ and kernel.order == 2 and kernel.param > 0 and
+                lib.dc_supports_tc_bytes(self.n, self.n_features, self.n_class, code, C.byref(nbytes)) == 0):
+            blob = torch.empty(nbytes.value + 128, dtype=torch.uint8, device=device)
+            ptr = (blob.data_ptr() + 127) // 128 * 128
+            s2, valid = C.c_double(), C.c_int32()
             with torch.cuda.device(device):
-                _lib.check(lib.dc_pack_supports_tc(s.data_ptr(), w.data_ptr(), self.n, self.n_features, tc_ptr,
+                _lib.check(lib.dc_pack_supports_tc(s.data_ptr(), w.data_ptr(), self.n, self.n_features, C.byref(kernel), ptr,
                                                    _stream_ptr(device)), "dc_pack_supports_tc")
-            s2max = float(s.double().square().sum(dim=1).max().item())
+                torch.cuda.current_stream(device).synchronize()
+                _lib.check(lib.dc_supports_tc_info(ptr, self.n, C.byref(s2), C.byref(valid)), "dc_supports_tc_info")
+            if valid.value:
+                self.tc_blob, tc_ptr, s2max, tc_gamma = blob, ptr, s2.value, float(kernel.param)
         self.desc = Supports(self.table.data_ptr(), self.n, self.n_features, self.n_class, f_pad.value, row.value, code, 0,
-                             tc_ptr, s2max)
+                             tc_ptr, s2max, tc_gamma)
 
 
 def score_grad(fk: FkDesc, kernel: KernelDesc, sv: SupportSet, q: torch.Tensor, grad_mode: int = DC_GRAD_NONE,

@@ -64,11 +64,13 @@ class _SupportCache:
     def _key(t):
         return (id(t), t._version, tuple(t.shape), t.dtype, t.device)
 
-    def get(self, name, feats, weights):
-        key = (self._key(feats), self._key(weights))
+    def get(self, name, feats, weights, kfun=None):
+        kdesc = getattr(kfun, "desc", None)
+        kkey = None if kdesc is None else (kdesc.kind, kdesc.order, kdesc.param)
+        key = (self._key(feats), self._key(weights), kkey)
         hit = self._entries.get(name)
         if hit is None or hit[0] != key:
-            hit = (key, functional.SupportSet(feats, weights))
+            hit = (key, functional.SupportSet(feats, weights, kernel=kdesc))
             self._entries[name] = hit
         return hit[1]
 
@@ -312,8 +314,8 @@ class DiffCo(Perceptron, _FusedScorer):
     # ------------------------------------------------------------------ scoring
     def _select(self, weights):
         if weights == "gains":
-            return self._cache.get("gains", self.support_transformed, self.gains), self.kernel_func
-        return self._cache.get("rbf", self.support_transformed, self.rbf_nodes), self.rbf_kernel
+            return self._cache.get("gains", self.support_transformed, self.gains, self.kernel_func), self.kernel_func
+        return self._cache.get("rbf", self.support_transformed, self.rbf_nodes, self.rbf_kernel), self.rbf_kernel
 
     def score(self, point):
         return self.score_original(point)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 2
+#define DC_ABI_VERSION 3
 
 #define DC_MAX_DOF 16
 #define DC_MAX_LINKS 16
@@ -123,6 +123,7 @@ typedef struct dc_supports {
   const void* tc_blob; /* device, optional (NULL = none): image written by dc_pack_supports_tc for the same S_feat / W */
   double tc_s2max;     /* max_n |s_n|^2 if known (> 0): lets dc_score_grad skip the tensor-core path when the kernel
                           width makes too many pairs "near" (they are re-evaluated exactly on the FP32 pipe); 0 = unknown */
+  double tc_gamma;     /* RQKernel gamma the image was packed for (the kernel width is folded into the operands) */
 } dc_supports;
 
 typedef enum dc_grad_mode {
@@ -143,19 +144,26 @@ int dc_pack_supports(const void* s_feat, const void* w, int64_t n, int32_t n_fea
                      void* table, dc_stream_t stream);
 
 /*
- * Tensor-core operand image of a support set (fp32, one class, n_features <= 14): dc_supports_tc_bytes gives the
- * buffer size (DC_ERR_UNSUPPORTED for shapes the tensor-core kernel does not cover), dc_pack_supports_tc fills a
- * 128-byte aligned device buffer from S_feat[N,F] and W[N].  Put the pointer into dc_supports.tc_blob.
+ * Tensor-core operand image of a support set (fp32, one class, n_features <= 14, RQKernel with p = 2):
+ * dc_supports_tc_bytes gives the buffer size (DC_ERR_UNSUPPORTED for shapes the tensor-core kernel does not cover),
+ * dc_pack_supports_tc fills a 128-byte aligned device buffer from S_feat[N,F], W[N] and the kernel (gamma and the
+ * weights are folded into the operands, so the image belongs to this (S, W, kernel) triple).  dc_supports_tc_info
+ * (synchronises; call once after packing) returns max|s|^2 and whether the scaled operands fit fp16's range — put the
+ * pointer into dc_supports.tc_blob, gamma into tc_gamma and max|s|^2 into tc_s2max only when `valid` is 1.
  */
 int dc_supports_tc_bytes(int64_t n, int32_t n_features, int32_t n_class, int32_t dtype, int64_t* bytes);
-int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_features, void* blob, dc_stream_t stream);
+int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_features, const dc_kernel_desc* kernel,
+                        void* blob, dc_stream_t stream);
+int dc_supports_tc_info(const void* blob, int64_t n, double* s2max, int32_t* valid);
 
 /* Process-wide tuning knobs (the only global state of the library besides the launch counter). */
 typedef enum dc_option {
   DC_OPT_TC_ENABLE = 1,   /* 0 / 1 (default 1; environment DIFFCO_B200_TC=0 also disables): use the tensor-core kernel */
   DC_OPT_TC_ERR_COEF = 2, /* bound on the error of the tensor-core rho, relative to |x|^2 + max|s|^2 (default 5e-7)     */
   DC_OPT_TC_TOL_PAIR = 3, /* admissible error of one pair's kernel value (default 2e-7): sets the near-pair threshold   */
-  DC_OPT_TC_MIN_BATCH = 4 /* smallest batch sent to the tensor-core kernel (default 4096)                               */
+  DC_OPT_TC_MIN_BATCH = 4, /* smallest batch sent to the tensor-core kernel (default 4096)                              */
+  DC_OPT_TC_STATS = 5,     /* set 1: (re)start counting the pairs re-evaluated exactly, 0: stop; get: the count (syncs)  */
+  DC_OPT_PEER_TIMEOUT_S = 6 /* seconds dc_peer_barrier spins before it gives up and traps (default 120)                  */
 } dc_option;
 int dc_set_option(int32_t option, double value);
 double dc_get_option(int32_t option);

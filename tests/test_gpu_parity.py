@@ -77,7 +77,7 @@ def oracle_score_grad(robot, kspec, S, W, q, go=None):
     return s.reshape(len(q), -1), g
 
 
-def cuda_support_set(robot, S, W, dtype, dev):
+def cuda_support_set(robot, S, W, dtype, dev, kfun=None):
     """Packed supports the way the product builds them: support_transformed = the device FK (dc_fk_forward) of the
     support configurations in the model dtype — the same device function the fused kernel runs on the queries, so a
     query that coincides with a support has r == 0 exactly, as in the reference (one fkine for both sides)."""
@@ -85,7 +85,10 @@ def cuda_support_set(robot, S, W, dtype, dev):
 
     St = Fn.fk_forward(robot.fk_desc, S.to(device=dev, dtype=dtype))
     assert rel(St, P.oracle_fk(robot)(S).reshape(len(S), -1)) <= (2e-6 if dtype == torch.float32 else 1e-13)
-    return Fn.SupportSet(St, W.to(dtype), dev)
+    from diffco_b200 import kernel as K
+
+    # the tensor-core operand image is built for one kernel (its width is folded in): the suite's "rq" unless told otherwise
+    return Fn.SupportSet(St, W.to(dtype), dev, kernel=(kfun or K.RQKernel(10.0)).desc)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -160,7 +160,7 @@ def test_out_of_range_queries_and_large_weights(dev, lib):
 
     kfun, kspec = K.RQKernel(40.0), O.KernelSpec("rq", 40.0, 2)
     fk = Fn.none_fk(6)
-    sv = Fn.SupportSet(S.float().to(dev), W.float().to(dev), dev)
+    sv = Fn.SupportSet(S.float().to(dev), W.float().to(dev), dev, kernel=kfun.desc)
     f = lambda z: O.score_original(z, lambda t: t, kspec, S.float().double(), W.float().double())
     s_ref, g_ref = O.score_and_grad(f, q.float().double())
     assert lib.dc_set_option(1, 1.0) == 0

@@ -90,13 +90,19 @@ def test_tensor_core_peer_and_trajectory_entry_points_validate_arguments(lib):
 
     n = C.c_int64()
     assert lib.dc_supports_tc_bytes(2000, 14, 1, _lib.DC_F32, C.byref(n)) == 0
-    assert n.value == 21 * 21888 + 32  # 21 chunks of 96 supports + the scale trailer
+    # 21 chunks of 96 supports: GEMM1 + GEMM2 images, fp32 weights, chunk maxima (padded to 4), trailer
+    assert n.value == 21 * (9216 + 12288) + (21 * 96 + 24) * 4 + 64
     assert lib.dc_supports_tc_bytes(2000, 15, 1, _lib.DC_F32, C.byref(n)) == -2   # F > 14
     assert lib.dc_supports_tc_bytes(2000, 14, 4, _lib.DC_F32, C.byref(n)) == -2   # multi-class
     assert lib.dc_supports_tc_bytes(2000, 14, 1, _lib.DC_F64, C.byref(n)) == -2   # float64
     assert lib.dc_supports_tc_bytes(0, 14, 1, _lib.DC_F32, C.byref(n)) == -1
-    assert lib.dc_pack_supports_tc(None, None, 10, 14, None, None) == -1
-    assert lib.dc_pack_supports_tc(64, 64, 10, 14, 72, None) == -1                # blob not 128-byte aligned
+    rq = _lib.KernelDesc(_lib.DC_K_RQ, 2, 10.0)
+    assert lib.dc_pack_supports_tc(None, None, 10, 14, C.byref(rq), None, None) == -1
+    assert lib.dc_pack_supports_tc(64, 64, 10, 14, C.byref(rq), 72, None) == -1   # blob not 128-byte aligned
+    assert lib.dc_pack_supports_tc(64, 64, 10, 14, None, 128, None) == -1         # the image is built for one kernel
+    ph = _lib.KernelDesc(_lib.DC_K_POLYHARMONIC, 1, 1.0)
+    assert lib.dc_pack_supports_tc(64, 64, 10, 14, C.byref(ph), 128, None) == -2  # RQKernel(p = 2) only
+    assert lib.dc_supports_tc_info(None, 10, None, None) == -1
     saved = [lib.dc_get_option(k) for k in (1, 2, 3, 4)]
     try:
         assert lib.dc_set_option(_lib.DC_OPT_TC_ERR_COEF, 1e-6) == 0 and lib.dc_get_option(_lib.DC_OPT_TC_ERR_COEF) == 1e-6

@@ -25,9 +25,10 @@ int main(int argc, char** argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 2000, B = argc > 2 ? atoi(argv[2]) : 65536, D = 7, F = 14;
   const int near_frac_pct = argc > 3 ? atoi(argv[3]) : 0;  // % of queries placed next to a support
   const double gamma = 10.0;
-  unsigned long long seed = 1234;
+  unsigned long long seed = argc > 5 ? strtoull(argv[5], nullptr, 10) : 1234;
+  const double spread = argc > 6 ? atof(argv[6]) : 1.0;  // joint-angle range of supports and queries, in units of pi
   std::vector<double> Sq(N * D), Sx(N * F), W(N), Q((size_t)B * D);
-  for (auto& v : Sq) v = (urand(seed) * 2 - 1) * M_PI;
+  for (auto& v : Sq) v = (urand(seed) * 2 - 1) * M_PI * spread;
   for (int n = 0; n < N; ++n) fk7(&Sq[n * D], &Sx[n * F]);
   for (auto& v : W) v = nrand(seed);
   for (size_t b = 0; b < (size_t)B; ++b) {
@@ -35,7 +36,7 @@ int main(int argc, char** argv) {
       const int n = (int)(urand(seed) * N) % N;
       for (int i = 0; i < D; ++i) Q[b * D + i] = Sq[n * D + i] + 0.02 * nrand(seed);
     } else {
-      for (int i = 0; i < D; ++i) Q[b * D + i] = (urand(seed) * 2 - 1) * M_PI;
+      for (int i = 0; i < D; ++i) Q[b * D + i] = (urand(seed) * 2 - 1) * M_PI * spread;
     }
   }
   if (near_frac_pct > 0) for (int i = 0; i < D; ++i) Q[5 * D + i] = Sq[17 * D + i];  // exact coincidence in fp32? (not exactly: FK in float)
@@ -57,7 +58,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(d_table, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_blob, 0, tc_blob_bytes(N)));
   CK(cudaMemset(d_out, 0, (size_t)B * 8 * 4));
-  if (launch_pack_supports_tc(d_s, d_w, N, F, d_blob, 0) != 0) { printf("pack failed\n"); return 1; }
+  if (launch_pack_supports_tc(d_s, d_w, N, F, (float)gamma, d_blob, 0) != 0) { printf("pack failed\n"); return 1; }
   CK(cudaDeviceSynchronize());
 
   TcArgs a;
@@ -69,9 +70,21 @@ int main(int argc, char** argv) {
   a.blob = d_blob; a.table = d_table; a.q = d_q; a.score = d_out; a.grad = d_out + 1; a.grad_out = nullptr; a.dbg = d_dbg;
   a.batch = B; a.score_ld = 8; a.grad_ld = 8; a.n_sv = N; a.n_feat = F; a.n_in = D; a.row_stride = 16; a.f_pad = 14;
   a.err_coef = argc > 4 ? (float)atof(argv[4]) : 1.0e-6f; a.tol_pair = 2e-7f;
+  unsigned long long* d_stats; CK(cudaMalloc(&d_stats, 8)); CK(cudaMemset(d_stats, 0, 8)); a.stats = d_stats;
   int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   int st = launch_score_tc<TC_GRAD>(a, sms, 0);
+  {
+    int nb = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_tc_kernel<TC_GRAD>, TcLayout::THREADS, TcLayout::SM_BYTES);
+    printf("occupancy: %d CTAs per SM (%d B dynamic smem per CTA)\n", nb, TcLayout::SM_BYTES);
+  }
   printf("launch status %d, tiles %d chunks %d smem %d\n", st, a.n_tiles, a.n_chunks, TcLayout::SM_BYTES);
+  {
+    float tr[TcLayout::TRAILER_FLOATS];
+    CK(cudaMemcpy(tr, tc_trailer(d_blob, N), sizeof(tr), cudaMemcpyDeviceToHost));
+    printf("trailer: max|s|^2 %.3f  max|w s| %.3f  max|s_f| %.3f  Sa %g  tau*c0 %g  tau %g  inv_g %g  gamma %g  valid %g\n", tr[0], tr[1],
+           tr[2], tr[3], tr[4], tr[5], tr[6], tr[7], tr[8]);
+  }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 2; }
 
@@ -123,24 +136,42 @@ int main(int argc, char** argv) {
     }
   }
   printf("score: max|err| %.3e / max|ref| %.3e = %.3e    grad: %.3e / %.3e = %.3e   (gate 1e-5)\n", serr, smax, serr / smax, gerr, gmax, gerr / gmax);
+  {
+    unsigned long long near = 0; CK(cudaMemcpy(&near, d_stats, 8, cudaMemcpyDeviceToHost));
+    printf("near pairs evaluated exactly: %llu of %.3e (%.4f %%), err_coef %.2e\n", near, (double)B * N, 100.0 * near / ((double)B * N), a.err_coef);
+    a.stats = nullptr;
+  }
+  if (getenv("TC_QUICK")) return 0;
 
   if (getenv("TC_TRACE")) {
-    long long* d_tr; CK(cudaMalloc(&d_tr, 64 * 16 * 8)); CK(cudaMemset(d_tr, 0, 64 * 16 * 8));
+    long long* d_tr; CK(cudaMalloc(&d_tr, (2048 + 4 * 1024) * 8)); CK(cudaMemset(d_tr, 0, (2048 + 4 * 1024) * 8));
     a.dbg = nullptr; a.trace = d_tr;
     launch_score_tc<TC_GRAD>(a, sms, 0); CK(cudaDeviceSynchronize());
     launch_score_tc<TC_GRAD>(a, sms, 0); CK(cudaDeviceSynchronize());
     std::vector<long long> tr(64 * 16); CK(cudaMemcpy(tr.data(), d_tr, tr.size() * 8, cudaMemcpyDeviceToHost));
     const long long b0 = tr[8];
-    printf("chunk | ctrl: full  g1iss  refill ccwait g2iss | query w0: start  full   rho    ld     comp   stdone\n");
+    printf("chunk | mma: ccwait g2iss g1iss(g+2) | query w0: start  b2full rho    ld     comp   stdone\n");
     for (int g = 0; g < 44; ++g) {
       printf("%3d  |", g);
-      for (int k : {0, 1, 2, 3, 4}) printf(" %6lld", tr[g * 16 + k] ? tr[g * 16 + k] - b0 : -1);
+      for (int k : {3, 4, 1}) printf(" %6lld", tr[g * 16 + k] ? tr[g * 16 + k] - b0 : -1);
       printf(" |");
       for (int k : {8, 9, 10, 11, 12, 13}) printf(" %6lld", tr[g * 16 + k] ? tr[g * 16 + k] - b0 : -1);
       printf("\n");
     }
-    printf("tile events (cycles rel. to chunk-0 start of tile 0): start, fk done, bar, loop end, drained, bar, epilogue done, bar, copied\n");
-    for (int ti = 0; ti < 3; ++ti) { printf("tile %d:", ti); for (int ev = 0; ev < 9; ++ev) printf(" %7lld", tr[(50 + ev) * 16 + ti] ? tr[(50 + ev) * 16 + ti] - b0 : -1); printf("\n"); }
+    printf("tile events (cycles rel. to chunk-0 start of tile 0): lower half: loop start, loop end, drained, next FK done | owners: loop start, loop end, drained, G ready, records, stored\n");
+    for (int ti = 0; ti < 3; ++ti) { printf("tile %d:", ti); for (int ev : {0, 1, 2, 3, 8, 9, 10, 11, 12, 13}) printf(" %7lld", tr[(50 + ev) * 16 + ti] ? tr[(50 + ev) * 16 + ti] - b0 : -1); printf("\n"); }
+    {
+      std::vector<long long> cr(4 * 1024); CK(cudaMemcpy(cr.data(), d_tr + 2048, cr.size() * 8, cudaMemcpyDeviceToHost));
+      const int grid = a.n_tiles < 2 * sms ? a.n_tiles : 2 * sms;
+      long long tmin = -1, tmax = 0; int per_sm[256] = {0};
+      for (int c = 0; c < grid; ++c) { if (tmin < 0 || cr[c * 4 + 1] < tmin) tmin = cr[c * 4 + 1]; if (cr[c * 4 + 2] > tmax) tmax = cr[c * 4 + 2]; per_sm[cr[c * 4] & 255]++; }
+      int hist[8] = {0}; for (int i = 0; i < 256; ++i) if (per_sm[i]) hist[per_sm[i] < 7 ? per_sm[i] : 7]++;
+      printf("CTA residency: grid %d, SMs with 1/2/3+ CTAs: %d/%d/%d, kernel span %.1f us\n", grid, hist[1], hist[2], hist[3] + hist[4], (tmax - tmin) * 1e-3);
+      double d1 = 0, d2 = 0, s1 = 0, s2 = 0; int n1 = 0, n2 = 0; long long late = 0;
+      for (int c = 0; c < grid; ++c) { const double st = (cr[c * 4 + 1] - tmin) * 1e-3, du = (cr[c * 4 + 2] - cr[c * 4 + 1]) * 1e-3; if (st > late) late = (long long)st;
+        if (cr[c * 4 + 3] == 1) { d1 += du; s1 += st; ++n1; } else { d2 += du; s2 += st; ++n2; } }
+      printf("  CTAs with 1 tile: %d, mean start %.1f us, mean duration %.1f us | with 2 tiles: %d, mean start %.1f us, mean duration %.1f us | latest start %lld us\n", n1, n1 ? s1 / n1 : 0., n1 ? d1 / n1 : 0., n2, n2 ? s2 / n2 : 0., n2 ? d2 / n2 : 0., late);
+    }
     a.trace = nullptr;
   }
   // ---- timing ------------------------------------------------------------------------------------------------
