@@ -82,6 +82,7 @@ class Supports(C.Structure):
         ("tc_blob", C.c_void_p),
         ("tc_s2max", C.c_double),
         ("tc_gamma", C.c_double),
+        ("table_lo", C.c_void_p),
     ]
 
 
@@ -132,6 +133,8 @@ PROTOTYPES = {
     "dc_kernel_matrix": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_fk_forward": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_fk_forward_split": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dc_pack_supports_lo": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_perceptron_train": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
@@ -141,7 +144,7 @@ PROTOTYPES = {
     "dc_peer_free": (C.c_int, [C.c_void_p]),
     "dc_peer_barrier": (C.c_int, [C.POINTER(PeerTable), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
     "dc_score_grad_bcast": (C.c_int, [C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p, C.c_int64,
-                                      C.POINTER(PeerTable), C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+                                      C.POINTER(PeerTable), C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_traj_step": (C.c_int, [C.POINTER(FkDesc), C.POINTER(TrajParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dc_fk_vjp": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -18,7 +18,8 @@ bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel
                               int grad_mode);
 int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q, int64_t batch,
                   void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out, int32_t grad_mode,
-                  int num_sms, cudaStream_t stream, const dc_peer_table* bcast = nullptr, int n_bcast = 0);
+                  int num_sms, cudaStream_t stream, const dc_peer_table* bcast = nullptr, int n_bcast = 0,
+                  void* mirror = nullptr);
 
 #define DC_TQ_DECL(name) int name(int n_feat, ScoreArgs<float>& a, int num_sms, cudaStream_t stream);
 DC_TQ_DECL(tq_rq2_c1_score)
@@ -159,7 +160,35 @@ __global__ void __launch_bounds__(128) fk_forward_kernel(const __grid_constant__
   T qv[DC_MAX_DOF];
 #pragma unroll
   for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < fk.dof) ? q[b * fk.dof + i] : (T)0;
-  fk_forward<T>(fk, qv, x + b * F, 1);
+  fk_features(fk, qv, x + b * F, 1);  // float32: evaluated in float64 and rounded once (dc_fk.cuh)
+}
+
+// float32 features as (hi, lo) pairs: x = hi + lo to ~1e-9 (hi is what fk_forward_kernel<float> returns)
+__global__ void __launch_bounds__(128) fk_forward_split_kernel(const __grid_constant__ dc_fk_desc fk, const float* __restrict__ q,
+                                                               long long batch, float* __restrict__ xh, float* __restrict__ xl) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int F = fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim;
+  if (fk.type == DC_FK_NONE) {
+    for (int f = 0; f < F; ++f) {
+      xh[b * F + f] = q[b * F + f];
+      xl[b * F + f] = 0.f;
+    }
+    return;
+  }
+  float qv[DC_MAX_DOF];
+#pragma unroll
+  for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < fk.dof) ? q[b * fk.dof + i] : 0.f;
+  fk_forward_f32x<true>(fk, qv, xh + b * F, 1, xl + b * F, 1);
+}
+
+// table_lo[n][row] = -s_lo[n][f] for f < F, zero elsewhere (same row layout as the packed support table)
+__global__ void pack_supports_lo_kernel(const float* __restrict__ s_lo, long long n, int F, int row, float* __restrict__ table_lo) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * row) return;
+  const long long r = idx / row;
+  const int e = (int)(idx - r * row);
+  table_lo[idx] = (e < F) ? -s_lo[r * F + e] : 0.f;
 }
 
 template <typename T>
@@ -179,7 +208,7 @@ __global__ void __launch_bounds__(128) fk_vjp_kernel(const __grid_constant__ dc_
     out[i] = (T)0;
   }
   for (int f = 0; f < F; ++f) gl[f] = gx[b * F + f];
-  fk_forward<T>(fk, qv, xl, 1);
+  fk_features(fk, qv, xl, 1);
   fk_vjp<T>(fk, qv, xl, 1, gl, 1, out);
   for (int i = 0; i < fk.dof; ++i) gq[b * fk.dof + i] = out[i];
 }
@@ -415,6 +444,28 @@ int dc_fk_forward(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dt
     fk_forward_kernel<double><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*fk, (const double*)q, batch, (double*)x_out);
   else
     return DC_ERR_INVALID_ARG;
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int dc_fk_forward_split(const dc_fk_desc* fk, const void* q, int64_t batch, void* x_hi, void* x_lo, dc_stream_t stream) {
+  if (!fk || !fk_valid(*fk)) return DC_ERR_INVALID_ARG;
+  if (batch == 0) return DC_OK;
+  if (batch < 0 || !q || !x_hi || !x_lo) return DC_ERR_INVALID_ARG;
+  const long long blocks = ceil_div64(batch, 128);
+  fk_forward_split_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*fk, (const float*)q, batch, (float*)x_hi, (float*)x_lo);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int dc_pack_supports_lo(const void* s_lo, int64_t n, int32_t n_features, int32_t n_class, void* table_lo, dc_stream_t stream) {
+  int32_t f_pad = 0, row = 0;
+  const int st = dc_supports_layout(n_features, n_class, DC_F32, &f_pad, &row);
+  if (st != DC_OK) return st;
+  if (n < 1 || !s_lo || !table_lo) return DC_ERR_INVALID_ARG;
+  const long long total = (long long)n * row;
+  pack_supports_lo_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)s_lo, n, n_features, row,
+                                                                                        (float*)table_lo);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -35,6 +35,28 @@ __device__ void fk_planar_fwd(const double* link, int n, const T* q, Strided<T> 
   }
 }
 
+// The same chain with everything in registers (fully unrolled, at most NMAX links; x[2 NMAX], unused entries 0).  The
+// expressions are those of fk_planar_fwd, so both produce bit-identical features.
+template <int NMAX, typename T>
+__device__ __forceinline__ void fk_planar_fwd_reg(const double* link, int n, const T* q, T* x) {
+  T th = 0, px = 0, py = 0;
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      th += q[i];
+      T s, c;
+      sincos_t(th, &s, &c);
+      px += (T)link[i] * c;
+      py += (T)link[i] * s;
+      x[2 * i] = px;
+      x[2 * i + 1] = py;
+    } else {
+      x[2 * i] = (T)0;
+      x[2 * i + 1] = (T)0;
+    }
+  }
+}
+
 // g_q[i] = sum_{j>=i} -gx_j (y_j - y_{i-1}) + gy_j (x_j - x_{i-1}); p_{-1} = (ox, oy).
 template <typename T>
 __device__ void fk_planar_vjp(int n, Strided<T> x, Strided<T> g, T ox, T oy, T* gq) {
@@ -48,6 +70,25 @@ __device__ void fk_planar_vjp(int n, Strided<T> x, Strided<T> g, T ox, T oy, T* 
     T qx = (i > 0) ? x[2 * i - 2] : ox;
     T qy = (i > 0) ? x[2 * i - 1] : oy;
     gq[i] = A + Gx * qy - Gy * qx;
+  }
+}
+
+// fk_planar_vjp with everything in registers (origin 0; fully unrolled, at most NMAX links; same expressions).
+template <int NMAX>
+__device__ __forceinline__ void fk_planar_vjp_reg(int n, const float* x, const float* g, float* gq) {
+  float A = 0.f, Gx = 0.f, Gy = 0.f;
+#pragma unroll
+  for (int i = NMAX - 1; i >= 0; --i) {
+    if (i < n) {
+      const float px = x[2 * i], py = x[2 * i + 1];
+      const float gx = g[2 * i], gy = g[2 * i + 1];
+      A += gy * px - gx * py;
+      Gx += gx;
+      Gy += gy;
+      const float qx = (i > 0) ? x[2 * (i > 0 ? i : 1) - 2] : 0.f;
+      const float qy = (i > 0) ? x[2 * (i > 0 ? i : 1) - 1] : 0.f;
+      gq[i] = A + Gx * qy - Gy * qx;
+    }
   }
 }
 
@@ -232,6 +273,94 @@ __device__ __noinline__ void fk_forward(const dc_fk_desc& fk, const T* q, T* xp,
     default:
       break;
   }
+}
+
+// sin / cos in float64 to ~1e-13 absolute — all the (hi, lo) float32 feature pairs need (lo is ~1e-7 of hi) — at a
+// fifth of the instruction count of libm's sincos: two-term Cody-Waite reduction to [-pi/4, pi/4], Taylor polynomials
+// (sin to x^15, cos to x^14: truncation < 5e-13 at pi/4).  Arguments here are sums of joint angles (|x| < a few hundred).
+__device__ __forceinline__ void sincos_fast64(double x, double* s, double* c) {
+  const double kd = rint(x * 0.63661977236758134308);        // x / (pi/2)
+  double r = fma(-kd, 1.57079632673412561417, x);            // pi/2 = P1 + P2, P1 exact in 33 bits
+  r = fma(-kd, 6.07710050650619224932e-11, r);
+  const double r2 = r * r;
+  double sp = 1.0 / 1307674368000.0;                         // 1/15!
+  sp = fma(sp, r2, -1.0 / 6227020800.0);
+  sp = fma(sp, r2, 1.0 / 39916800.0);
+  sp = fma(sp, r2, -1.0 / 362880.0);
+  sp = fma(sp, r2, 1.0 / 5040.0);
+  sp = fma(sp, r2, -1.0 / 120.0);
+  sp = fma(sp, r2, 1.0 / 6.0);
+  sp = fma(-sp * r2, r, r);                                  // r - r^3 (1/6 - ...)
+  double cp = -1.0 / 87178291200.0;                          // -1/14!
+  cp = fma(cp, r2, 1.0 / 479001600.0);
+  cp = fma(cp, r2, -1.0 / 3628800.0);
+  cp = fma(cp, r2, 1.0 / 40320.0);
+  cp = fma(cp, r2, -1.0 / 720.0);
+  cp = fma(cp, r2, 1.0 / 24.0);
+  cp = fma(cp, r2, -0.5);
+  cp = fma(cp, r2, 1.0);
+  const int k = (int)kd;
+  const double s0 = (k & 1) ? cp : sp, c0 = (k & 1) ? sp : cp;
+  *s = (k & 2) ? -s0 : s0;
+  *c = ((k + 1) & 2) ? -c0 : c0;
+}
+
+// The planar chain in float64 with sincos_fast64, everything in registers: THE evaluation behind the float32 features of
+// RevolutePlanarRobot (tensor-core kernel's tile prologue, fk_forward_f32x) — one function, so features are bit-identical
+// wherever they are computed.
+template <int NMAX>
+__device__ __forceinline__ void fk_planar_f64_reg(const double* link, int n, const float* q, double* x) {
+  double th = 0.0, px = 0.0, py = 0.0;
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      th += (double)q[i];
+      double s, c;
+      sincos_fast64(th, &s, &c);
+      px = fma(link[i], c, px);
+      py = fma(link[i], s, py);
+      x[2 * i] = px;
+      x[2 * i + 1] = py;
+    } else {
+      x[2 * i] = 0.0;
+      x[2 * i + 1] = 0.0;
+    }
+  }
+}
+
+// float32 FEATURES from a float64 evaluation of the map on the same float32 configuration: hi = fl32(x), and (WITH_LO)
+// lo = fl32(x - hi).  A float32 chain accumulates ~1e-6 of absolute error over seven joints (angle sums up to 7 pi,
+// positions up to 7 link lengths); next to a support vector that alone is several 1e-5 of the gradient maximum for ANY
+// float32 evaluation (tests/test_gpu_tc_stress.py).  Evaluating in float64 leaves only the final rounding (hi), and the
+// exact near-pair path of the tensor-core kernel adds lo back, so differences x - s are good to ~1e-9.  Every float32
+// kernel and dc_fk_forward use THIS function, so a query that coincides with a support has bit-identical features.
+template <bool WITH_LO>
+__device__ __noinline__ void fk_forward_f32x(const dc_fk_desc& fk, const float* q, float* xh, int ldh, float* xl, int ldl) {
+  double qd[DC_MAX_DOF], xd[DC_MAX_FEATURES];
+  if (fk.type == DC_FK_PLANAR_CHAIN && fk.n_links <= 8) {
+    fk_planar_f64_reg<8>(fk.link_length, fk.n_links, q, xd);
+  } else {
+#pragma unroll
+    for (int i = 0; i < DC_MAX_DOF; ++i) qd[i] = (i < fk.dof) ? (double)q[i] : 0.0;
+    fk_forward<double>(fk, qd, xd, 1);
+  }
+  const int F = fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim;
+  for (int f = 0; f < F; ++f) {
+    const float h = (float)xd[f];
+    xh[(size_t)f * ldh] = h;
+    if (WITH_LO) xl[(size_t)f * ldl] = (float)(xd[f] - (double)h);
+  }
+}
+// the feature map as the kernels of element type T evaluate it
+__device__ __forceinline__ void fk_features(const dc_fk_desc& fk, const float* q, float* x, int ld) {
+  if (fk.type == DC_FK_NONE) {
+    for (int i = 0; i < fk.dof; ++i) x[(size_t)i * ld] = q[i];
+  } else {
+    fk_forward_f32x<false>(fk, q, x, ld, nullptr, 0);
+  }
+}
+__device__ __forceinline__ void fk_features(const dc_fk_desc& fk, const double* q, double* x, int ld) {
+  fk_forward<double>(fk, q, x, ld);
 }
 
 template <typename T>

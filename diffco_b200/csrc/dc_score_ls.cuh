@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kLsWarps * 32) score_ls_kernel(const __grid_co
       } else {
 #pragma unroll
         for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < a.n_in) ? qp[i] : (T)0;
-        fk_forward<T>(a.fk, qv, &xs[lead][0], 1);
+        fk_features(a.fk, qv, &xs[lead][0], 1);
       }
     } else {
       for (int f = 0; f < F; ++f) xs[lead][f] = (T)0;

@@ -94,16 +94,31 @@ bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel
   return true;
 }
 
+// Device-visible alias of a pinned (page-locked, mapped) host pointer; device pointers are returned unchanged; nullptr for
+// pageable host memory.
+static void* device_alias(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  if (at.type == cudaMemoryTypeHost) return at.devicePointer;
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return const_cast<void*>(p);
+  return nullptr;
+}
+
 int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q, int64_t batch,
                   void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out, int32_t grad_mode,
-                  int num_sms, cudaStream_t stream, const dc_peer_table* bcast, int n_bcast) {
+                  int num_sms, cudaStream_t stream, const dc_peer_table* bcast, int n_bcast, void* mirror) {
   TcArgs a;
+  a.mirror = static_cast<float*>(mirror);
   a.n_bcast = n_bcast;
   for (int k = 0; k < DC_MAX_PEERS; ++k) a.bcast[k] = (bcast && k < n_bcast) ? static_cast<float*>(bcast->ptr[k]) : nullptr;
   a.fk = *fk;
   if (!make_radial_consts<float>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
   a.blob = static_cast<const unsigned char*>(sv->tc_blob);
   a.table = static_cast<const float*>(sv->table);
+  a.table_lo = static_cast<const float*>(sv->table_lo);
   a.q = static_cast<const float*>(q);
   a.score = static_cast<float*>(score);
   a.grad = static_cast<float*>(grad);
@@ -163,7 +178,7 @@ int dc_supports_tc_info(const void* blob, int64_t n, double* s2max, int32_t* val
 
 int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
                         int64_t batch, const dc_peer_table* outs, int32_t n_outs, int64_t row_offset, int32_t grad_mode,
-                        dc_stream_t stream) {
+                        void* mirror, dc_stream_t stream) {
   if (!fk || !kernel || !sv || !outs || n_outs < 1 || n_outs > DC_MAX_PEERS || row_offset < 0) return DC_ERR_INVALID_ARG;
   if (batch == 0) return DC_OK;
   if (batch < 0 || !q || !sv->table) return DC_ERR_INVALID_ARG;
@@ -176,10 +191,14 @@ int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, cons
     (void)cudaGetLastError();
     return DC_ERR_NO_DEVICE;
   }
+  // q and mirror may be pinned host buffers (zero-copy: the kernel moves whole tiles with coalesced 16-byte accesses)
+  const void* qd = device_alias(q);
+  void* md = mirror ? device_alias(mirror) : nullptr;
+  if (!qd || (mirror && !md)) return DC_ERR_INVALID_ARG;
   const int64_t rec = 1 + (grad_mode == DC_GRAD_SUM ? fk->dof : 0);
   float* mine = static_cast<float*>(outs->ptr[0]) + row_offset * rec;  // the kernel adds (mine - outs[0]) to every base
-  return tc_score_grad(fk, kernel, sv, q, batch, mine, rec, grad_mode == DC_GRAD_SUM ? mine + 1 : nullptr, rec, nullptr,
-                       grad_mode, num_sms, (cudaStream_t)stream, outs, n_outs);
+  return tc_score_grad(fk, kernel, sv, qd, batch, mine, rec, grad_mode == DC_GRAD_SUM ? mine + 1 : nullptr, rec, nullptr,
+                       grad_mode, num_sms, (cudaStream_t)stream, outs, n_outs, md);
 }
 
 int dc_set_option(int32_t option, double value) { return tc_set_option(option, value); }

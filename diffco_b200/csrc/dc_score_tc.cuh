@@ -37,6 +37,16 @@
 #include "dc_fk.cuh"
 #include "dc_radial.cuh"
 
+// Experiment switches (tools/probe builds set them; the defaults are what the library ships).  Measured on B200 at
+// BASELINE configs[1] (profiles/r02g_variants.txt): both alternatives lose — the kernel is bound by issue slots and
+// dependency latency at 4 warps per scheduler, not by the XU pipe nor by the two halves stalling in lockstep.
+#ifndef DC_TC_INTPACK
+#define DC_TC_INTPACK 0   // 1: f16 operand words built with integer ops instead of F2FP (frees the XU pipe): 105.7 us vs 92.9 us
+#endif
+#ifndef DC_TC_DEPHASE
+#define DC_TC_DEPHASE 0   // 1: the owner half starts each tile half a chunk behind the lower half: 93.6 us vs 92.9 us
+#endif
+
 namespace dc {
 
 struct TcLayout {
@@ -61,7 +71,9 @@ struct TcLayout {
   static constexpr int COL_STAGE = NC;
   static constexpr int COL_G = 2 * COL_STAGE;  // 192 .. 223, 224 .. 255
   static constexpr int TMEM_COLS = 256;
-  static constexpr int QCAP = 64;    // near-pair queue entries per warp
+  // near-pair queue entries per warp: large enough that queues are normally drained once, at the end of the tile — a
+  // drain in the middle of the chunk loop stalls its warp for ~1500 cycles and, through the chunk barriers, the whole CTA
+  static constexpr int QCAP = 192;
   static constexpr int QWARPS = 8;   // query warps: 4 TMEM lane quarters x 2 column halves
   static constexpr int QTHREADS = QWARPS * 32;
   static constexpr int CTRL_WARP = QWARPS;
@@ -74,9 +86,11 @@ struct TcLayout {
   static constexpr int SM_RING2 = SM_RING1 + RS1 * B1_BYTES;
   static constexpr int SM_A = SM_RING2 + RS2 * B2_BYTES;    // A [K1/8][128][8] f16
   static constexpr int SM_XS = SM_A + TM * K1 * 2;          // features [2][128][16] f32 (near-pair path, epilogue)
+  static constexpr int XLO_SCALE_LOG2 = 22;                 // low parts are kept as f16 of 2^22 lo (|lo| <= ulp(hi) / 2)
   // exact-path accumulators: score [8][32], feature gradient [8][32][16] (non-owner warps first); the owners' half
   // (+ 512 bytes) doubles as the output records [128][17] once the owners have read it
-  static constexpr int SM_ACC = SM_XS + 2 * TM * 16 * 4;
+  static constexpr int SM_XLO = SM_XS + 2 * TM * 16 * 4;    // low parts of the features [2][128][16] f16 (near-pair path)
+  static constexpr int SM_ACC = SM_XLO + 2 * TM * 16 * 2;
   static constexpr int ACC_BYTES = QWARPS * 32 * 4 + QWARPS * 32 * 16 * 4 + 512;
   static constexpr int SM_QS = SM_ACC + ACC_BYTES;          // staged configurations [2][128][QS_DOF]
   static constexpr int SM_ROWS = SM_QS + 2 * TM * QS_DOF * 4;  // lower-half partial scores [128], |x|^2 [2][128]
@@ -91,6 +105,7 @@ struct TcArgs {
   RadialConsts<float> rc;
   const unsigned char* blob;  // [n_chunks x B1][n_chunks x B2][weights][chunk max|s|^2][trailer]
   const float* table;         // packed [-s | w] rows (dc_pack_supports), for the exact near-pair path
+  const float* table_lo;      // optional: low parts -(s - fl32(s)) in the same row layout (dc_pack_supports_lo)
   const float* q;
   float* score;
   float* grad;
@@ -110,6 +125,8 @@ struct TcArgs {
   int n_chunks;
   float* bcast[DC_MAX_PEERS];  // n_bcast > 0: every fused record block is stored into each of these (row 0 = row 0 of the
   int n_bcast;                 // gathered buffer; `score` then points at THIS rank's block of the first one)
+  float* mirror;               // optional: this launch's records are ALSO written here, row 0 = first query of the launch
+                               // (a mapped pinned host buffer: the end-to-end path of the multi-GPU scorer)
   float err_coef;  // delta(rho) <= err_coef * (|x|^2 + max_chunk |s|^2)
   float tol_pair;  // admissible |w|-relative error of one pair
 };
@@ -240,6 +257,16 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   return r;
 }
 __device__ __forceinline__ float pow2_floor(float v) { return __uint_as_float(__float_as_uint(v) & 0x7f800000u); }
+
+__host__ __device__ inline int tc_n_chunks(long long n_sv) { return (int)((n_sv + TcLayout::NC - 1) / TcLayout::NC); }
+__host__ __device__ inline size_t tc_trailer_offset(long long n_sv) {
+  const size_t nch = (size_t)tc_n_chunks(n_sv);
+  return nch * (TcLayout::B1_BYTES + TcLayout::B2_BYTES) + (nch * TcLayout::NC + ((nch + 3) & ~(size_t)3)) * 4;
+}
+__host__ __device__ inline size_t tc_blob_bytes(long long n_sv) { return tc_trailer_offset(n_sv) + TcLayout::TRAILER_FLOATS * 4; }
+__host__ __device__ inline const float* tc_trailer(const void* blob, long long n_sv) {
+  return reinterpret_cast<const float*>(static_cast<const unsigned char*>(blob) + tc_trailer_offset(n_sv));
+}
 
 // ---- pack: support vectors -> operand images ----------------------------------------------------------------------
 // trailer[0..2] = max |s|^2, max |w| max(1, max_f |s_f|), max |s_f| (as int bit patterns; zeroed by the caller)
@@ -377,61 +404,408 @@ enum TcMode { TC_SCORE = 0, TC_GRAD = 1 };
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // named barriers (0 is __syncthreads)
-enum { TCB_FK = 1, TCB_EPI = 2, TCB_OWN = 3, TCB_LOW = 4, TCB_ACC = 5, TCB_END = 6 };
+enum { TCB_FK = 1, TCB_EPI = 2, TCB_OWN = 3, TCB_LOW = 4, TCB_ACC = 5, TCB_END = 6, TCB_PHASE = 7 };
 
-// Exact evaluation of queued near pairs: half-warp h takes one entry, lane f of the half takes feature f (direct
-// difference against the fp32 support row), the 16 squares are summed with shuffles, and the pair's score / feature-
-// gradient terms are added to the WARP'S OWN shared-memory accumulators of that row, strictly in queue (= column)
-// order — so a row's result does not depend on its position in the batch nor on timing.  Four entries per half-warp
-// are in flight at once; the rows were prefetched into L1 when the pairs were queued.
-__device__ __noinline__ void tc_drain_pairs(const TcArgs& a, const uint32_t* queue, int count, const float* xs,
-                                            float* gacc_w, float* sacc_w, int lane) {
-  const int h = lane >> 4, f = lane & 15;
-  constexpr int U = 4;
-  for (int head = 0; head < count; head += 2 * U) {
-    bool valid[U];
-    int row[U];
-    float xv[U], tv[U];
+// Exact evaluation of queued near pairs, one pair per lane: the lane reads its query's features (shared memory) and the
+// fp32 support row [-s | w] (global; prefetched into L1 when the pair was queued; all loads of the batch are in flight
+// together), evaluates the pair with direct differences — the same arithmetic as the FP32-pipe kernels — and adds its
+// score / feature-gradient terms to the WARP'S OWN shared-memory accumulators of that row.  Entries of one row are
+// applied strictly in queue (= column) order: lanes holding the same row take turns (match.any groups them; almost
+// always a single round), so a row's result depends neither on its position in the batch nor on timing.
+// (Out of line, and it re-derives its shared-memory pointers from (warp, tile parity): the chunk loop that calls it keeps
+// as little state alive across the call as possible.)
+__device__ __noinline__ void tc_drain_pairs(const TcArgs& a, int count, int warp, int buf) {
+  using L = TcLayout;
+  constexpr int FM = TcLayout::FMAX;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const uint32_t* queue = reinterpret_cast<const uint32_t*>(smem + L::SM_QUEUE) + warp * L::QCAP;
+  const float* xs = reinterpret_cast<const float*>(smem + L::SM_XS) + buf * L::TM * 16;
+  const __half* xlo = reinterpret_cast<const __half*>(smem + L::SM_XLO) + buf * L::TM * 16;
+  float* sacc_w = reinterpret_cast<float*>(smem + L::SM_ACC) + warp * 32;
+  float* gacc_w = reinterpret_cast<float*>(smem + L::SM_ACC) + L::QWARPS * 32 + warp * 32 * 16;
+  const float lo_scale = 1.f / (float)(1 << TcLayout::XLO_SCALE_LOG2);
+  for (int head = 0; head < count; head += 32) {
+    const bool valid = head + lane < count;
+    const uint32_t e = queue[valid ? head + lane : head];
+    const int row = (int)(e >> 24), n = (int)(e & 0xffffffu);
+    const float4* tr = reinterpret_cast<const float4*>(a.table + (size_t)n * a.row_stride);  // 16-byte aligned rows
+    const float4* xr = reinterpret_cast<const float4*>(xs + row * 16);
+    float t[16], x[16];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = head + 2 * u + h;
-      valid[u] = idx < count;
-      const uint32_t e = queue[valid[u] ? idx : head];
-      row[u] = (int)(e >> 24);
-      const int n = (int)(e & 0xffffffu);
-      xv[u] = xs[row[u] * 16 + f];
-      tv[u] = (f < a.row_stride) ? a.table[(size_t)n * a.row_stride + f] : 0.f;  // [-s | w] row
+    for (int v = 0; v < 4; ++v) {
+      const float4 tv = (4 * v < a.row_stride) ? tr[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xv = xr[v];
+      t[4 * v] = tv.x, t[4 * v + 1] = tv.y, t[4 * v + 2] = tv.z, t[4 * v + 3] = tv.w;
+      x[4 * v] = xv.x, x[4 * v + 1] = xv.y, x[4 * v + 2] = xv.z, x[4 * v + 3] = xv.w;
     }
+    float wv = 0.f;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float d = (f < a.n_feat) ? xv[u] + tv[u] : 0.f;
-      float rho = d * d;
-      rho += __shfl_xor_sync(0xffffffffu, rho, 8);
-      rho += __shfl_xor_sync(0xffffffffu, rho, 4);
-      rho += __shfl_xor_sync(0xffffffffu, rho, 2);
-      rho += __shfl_xor_sync(0xffffffffu, rho, 1);
-      const float wv = __shfl_sync(0xffffffffu, tv[u], a.f_pad, 16);
-      float k, coef;
-      radial_eval<KR_RQ2, float>(a.rc, rho, k, coef);
-      const int r = row[u] & 31;
-      const float cg = wv * coef * d, cs = wv * k;
+    for (int f = 0; f < 16; ++f) wv = (f == a.f_pad) ? t[f] : wv;  // the weight sits right after the padded features
+    // low parts: x = x_hi + x_lo and s = s_hi + s_lo from the float64 feature map, so that the difference is good to ~1e-9
+    // even when the pair is 1e-3 apart (a float32 feature alone is off by up to half an ulp of ITS magnitude)
+    float lo[16];
+    {
+      const uint4* lr = reinterpret_cast<const uint4*>(xlo + row * 16);
+      const uint4 l0 = lr[0], l1 = lr[1];
+      const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
-      for (int ph = 0; ph < 2; ++ph) {  // entry 2u before entry 2u + 1
-        if (h == ph && valid[u]) {
-          if (f < a.n_feat) gacc_w[r * 16 + f] += cg;
-          if (f == 15) sacc_w[r] += cs;
-        }
-        __syncwarp();
+      for (int v = 0; v < 8; ++v) {
+        const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&lw[v]));
+        lo[2 * v] = p.x * lo_scale;
+        lo[2 * v + 1] = p.y * lo_scale;
       }
+    }
+    if (a.table_lo != nullptr) {
+      const float4* tl = reinterpret_cast<const float4*>(a.table_lo + (size_t)n * a.row_stride);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 tv = (4 * v < a.row_stride) ? tl[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+        lo[4 * v] += tv.x, lo[4 * v + 1] += tv.y, lo[4 * v + 2] += tv.z, lo[4 * v + 3] += tv.w;
+      }
+    }
+    float d[FM], rho = 0.f;
+#pragma unroll
+    for (int f = 0; f < FM; ++f) {
+      d[f] = (f < a.n_feat) ? (x[f] + t[f]) + lo[f] : 0.f;
+      rho = fmaf(d[f], d[f], rho);
+    }
+    float k, coef;
+    radial_eval<KR_RQ2, float>(a.rc, rho, k, coef);
+    const float cg = wv * coef, cs = wv * k;
+    const int r = row & 31;
+    // lanes with the same row: the one with the fewest lower-numbered peers goes first
+    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? r : 32 + lane);
+    int turn = __popc(peers & ((1u << lane) - 1u));
+    uint32_t pending = __ballot_sync(0xffffffffu, valid);
+    while (pending != 0) {
+      if (valid && turn == 0) {
+        float4* g4 = reinterpret_cast<float4*>(gacc_w + r * 16);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float4 g = g4[v];
+          if (4 * v + 0 < FM) g.x = fmaf(cg, d[4 * v + 0 < FM ? 4 * v + 0 : 0], g.x);
+          if (4 * v + 1 < FM) g.y = fmaf(cg, d[4 * v + 1 < FM ? 4 * v + 1 : 0], g.y);
+          if (4 * v + 2 < FM) g.z = fmaf(cg, d[4 * v + 2 < FM ? 4 * v + 2 : 0], g.z);
+          if (4 * v + 3 < FM) g.w = fmaf(cg, d[4 * v + 3 < FM ? 4 * v + 3 : 0], g.w);
+          g4[v] = g;
+        }
+        sacc_w[r] += cs;
+      }
+      --turn;
+      __syncwarp();
+      pending = __ballot_sync(0xffffffffu, valid && turn >= 0);
     }
   }
   if (a.stats != nullptr && lane == 0) atomicAdd(a.stats, (unsigned long long)count);
 }
 
+// ---- lower half of the query warps: configurations of tile ti -> FK (float64) -> features (hi, lo), |x|^2, A operand ----------
+// Out of line on purpose: its register needs (float64 sincos chain) must not leak into the allocation of the chunk loop.
+// It re-derives what it needs (tile range, scales) instead of taking it from the caller, for the same reason.
+__device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
+  using L = TcLayout;
+  constexpr int NC = L::NC, FM = L::FMAX, QT = L::QTHREADS, TM = L::TM;
+  (void)NC;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int row = tid, lane = tid & 31, warp = tid >> 5;
+  (void)lane;
+  (void)warp;
+  uint64_t* bar_a = reinterpret_cast<uint64_t*>(smem + L::SM_BAR) + 10;
+  unsigned char* a_op = smem + L::SM_A;
+  float* xs_all = reinterpret_cast<float*>(smem + L::SM_XS);
+  __half* xlo_all = reinterpret_cast<__half*>(smem + L::SM_XLO);
+  float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);
+  float* xx_all = reinterpret_cast<float*>(smem + L::SM_ROWS) + TM;
+  const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
+#ifdef DC_TC_ENABLE_TRACE
+  const int nch = a.n_chunks;
+#endif
+  const float* trailer = tc_trailer(a.blob, a.n_sv);
+  const float sa = trailer[3], tc0 = trailer[4];
+  const int F = a.n_feat;
+  const bool has_fk = a.fk.type != DC_FK_NONE;
+  const int buf = ti & 1;
+  const long long b_base = (t0 + ti) * TM;
+  const int nq = (int)min((long long)TM, a.batch - b_base);
+  float* xs = xs_all + buf * TM * 16;
+  float* qs = qs_all + buf * TM * L::QS_DOF;
+  const float* src = a.q + (size_t)b_base * a.n_in;
+  const int n_words = nq * a.n_in;
+  float x[FM], xlo[FM];  // features as float32 (hi, lo) pairs of a float64 evaluation (dc_fk.cuh: fk_forward_f32x)
+  float qv[DC_MAX_DOF];
+  if (has_fk) {
+    // coalesced staging of the tile's configurations (also what makes zero-copy reads of pinned host memory efficient)
+    if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int i = tid; i < n_words / 4; i += TM) reinterpret_cast<float4*>(qs)[i] = s4[i];
+    } else {
+      for (int i = tid; i < n_words; i += TM) qs[i] = src[i];
+    }
+    named_sync(TCB_LOW, TM);
+#pragma unroll
+    for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (row < nq && i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
+    if (a.fk.type == DC_FK_PLANAR_CHAIN) {
+      // the BASELINE robot: the chain in registers, float64 with the short sincos (== fk_forward_f32x's planar branch)
+      double xd[16];
+      fk_planar_f64_reg<8>(a.fk.link_length, a.fk.n_links, qv, xd);
+#pragma unroll
+      for (int f = 0; f < FM; ++f) {
+        x[f] = (float)xd[f];
+        xlo[f] = (float)(xd[f] - (double)x[f]);
+      }
+    } else {
+      float xh16[DC_MAX_DOF], xl16[DC_MAX_DOF];
+#pragma unroll
+      for (int i = 0; i < DC_MAX_DOF; ++i) xh16[i] = xl16[i] = 0.f;
+      if (row < nq) fk_forward_f32x<true>(a.fk, qv, xh16, 1, xl16, 1);
+#pragma unroll
+      for (int f = 0; f < FM; ++f) {
+        x[f] = (f < F) ? xh16[f] : 0.f;
+        xlo[f] = (f < F) ? xl16[f] : 0.f;
+      }
+    }
+  } else {
+    // transform=None: the rows ARE the features; staged straight into the feature layout [128][16]
+    for (int i = tid; i < TM * 16; i += TM) xs[i] = 0.f;
+    named_sync(TCB_LOW, TM);
+    for (int i = tid; i < n_words; i += TM) {
+      const int r = i / a.n_in;
+      xs[r * 16 + (i - r * a.n_in)] = src[i];
+    }
+    named_sync(TCB_LOW, TM);
+#pragma unroll
+    for (int f = 0; f < FM; ++f) {
+      x[f] = xs[row * 16 + f];
+      xlo[f] = 0.f;
+    }
+  }
+  {
+    const float sc = (float)(1 << L::XLO_SCALE_LOG2);
+    uint4* lr = reinterpret_cast<uint4*>(xlo_all + (buf * TM + row) * 16);
+    uint4 l0, l1;
+    l0.x = pack_f16x2(xlo[0] * sc, xlo[1] * sc), l0.y = pack_f16x2(xlo[2] * sc, xlo[3] * sc);
+    l0.z = pack_f16x2(xlo[4] * sc, xlo[5] * sc), l0.w = pack_f16x2(xlo[6] * sc, xlo[7] * sc);
+    l1.x = pack_f16x2(xlo[8] * sc, xlo[9] * sc), l1.y = pack_f16x2(xlo[10] * sc, xlo[11] * sc);
+    l1.z = pack_f16x2(xlo[12] * sc, xlo[13] * sc), l1.w = 0u;
+    lr[0] = l0;
+    lr[1] = l1;
+  }
+  float xx = 0.f, xamax = 0.f;
+#pragma unroll
+  for (int f = 0; f < FM; ++f) {
+    xx = fmaf(x[f], x[f], xx);
+    xamax = fmaxf(xamax, fabsf(x[f]));
+  }
+  {
+    float4* xr = reinterpret_cast<float4*>(xs + row * 16);
+    xr[0] = make_float4(x[0], x[1], x[2], x[3]);
+    xr[1] = make_float4(x[4], x[5], x[6], x[7]);
+    xr[2] = make_float4(x[8], x[9], x[10], x[11]);
+    xr[3] = make_float4(x[12], x[13], 0.f, 0.f);
+  }
+  // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
+  const bool in_range = (sa * xamax < 32768.f) && (tc0 * xx < 32768.f);
+  {
+    float v[L::K1];
+    const float XX = in_range ? tc0 * xx : 0.f;
+#pragma unroll
+    for (int k = 0; k < L::K1; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int f = 0; f < FM; ++f) {
+      const float xsc = in_range ? sa * x[f] : 0.f;
+      const float hi = split_hi(xsc);
+      v[f] = hi;                       // x beta s_h
+      v[16 + f] = (xsc - hi) * 256.f;  // x beta s_h / 256
+      v[32 + f] = hi * (1.f / 256.f);  // x 256 (beta s)_lo
+    }
+    const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
+    v[14] = 1.f;  // x S1   (S = tau (1 + c0 |s|^2), three terms)
+    v[15] = 1.f;  // x S2
+    v[30] = 1.f;  // x S3
+    v[31] = x1;   // x 1
+    v[46] = x2;   // x 1
+    v[47] = x3;   // x 1
+#pragma unroll
+    for (int kc = 0; kc < L::K1 / 8; ++kc) {
+      uint4 pk;
+      pk.x = pack_f16x2(v[8 * kc + 0], v[8 * kc + 1]);
+      pk.y = pack_f16x2(v[8 * kc + 2], v[8 * kc + 3]);
+      pk.z = pack_f16x2(v[8 * kc + 4], v[8 * kc + 5]);
+      pk.w = pack_f16x2(v[8 * kc + 6], v[8 * kc + 7]);
+      reinterpret_cast<uint4*>(a_op)[kc * TM + row] = pk;
+    }
+  }
+  fence_proxy_async();
+  mbar_arrive(bar_a);
+  xx_all[buf * TM + row] = in_range ? xx : -1.f;
+#ifdef DC_TC_ENABLE_TRACE
+  if (a.dbg != nullptr && t0 + ti == 0) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a.dbg[(size_t)TM * (nch * NC) + TM * 32 + row * 16 + c] = c < FM ? x[c] : 0.f;
+  }
+#endif
+  named_arrive(TCB_FK, QT);  // features, |x|^2 (and the staged configurations) of tile ti are visible to the owners
+}
+
+// ---- epilogue of tile ti (owner half of the query warps): G from TMEM, feature gradient, J_FK^T, records -> memory -----------
+// Out of line like tc_fk_stage: its register arrays must not shape the allocation of the chunk loop.  `sc_hi` is the
+// caller's partial score (upper column half); everything else is re-derived.
+template <int MODE>
+__device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, float sc_hi) {
+  using L = TcLayout;
+  constexpr int NC = L::NC, FM = L::FMAX, QT = L::QTHREADS, TM = L::TM;
+  (void)NC;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = ((warp & 3) << 5) | lane;
+  const int buf = ti & 1;
+  uint64_t* bar_g = reinterpret_cast<uint64_t*>(smem + L::SM_BAR) + 11;
+  const uint32_t tmem = *reinterpret_cast<const uint32_t*>(smem + L::SM_TMEM_SLOT);
+  const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const float* xs = reinterpret_cast<const float*>(smem + L::SM_XS) + buf * TM * 16;
+  float* sacc = reinterpret_cast<float*>(smem + L::SM_ACC);
+  float* gacc = sacc + L::QWARPS * 32;
+  float* os = gacc + 4 * 32 * 16;
+  float* sacc_w = sacc + warp * 32;
+  float* gacc_w = gacc + warp * 32 * 16;
+  float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);
+  const float* sc_p = reinterpret_cast<const float*>(smem + L::SM_ROWS);
+  const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
+  const long long b_base = (t0 + ti) * TM;
+  const int nq = (int)min((long long)TM, a.batch - b_base);
+  const int F = a.n_feat;
+  const int n_out = 1 + (MODE == TC_GRAD ? a.n_in : 0);
+  const bool fused = (MODE == TC_GRAD) ? (a.score_ld == a.grad_ld && a.score_ld == n_out && a.grad == a.score + 1)
+                                       : (a.score_ld == 1);
+  const bool has_fk = a.fk.type != DC_FK_NONE;
+  const float inv_g = tc_trailer(a.blob, a.n_sv)[6];
+#ifdef DC_TC_ENABLE_TRACE
+  const int nch = a.n_chunks;
+#endif
+  const P2 sc2(sc_hi, 0.f);
+  // ---- epilogue (owners): G from TMEM, feature gradient, J_FK^T, records into shared memory ------------------------
+  named_sync(TCB_EPI, QT);
+  float gx[DC_MAX_DOF], xl[DC_MAX_DOF];
+#pragma unroll
+  for (int i = 0; i < DC_MAX_DOF; ++i) {
+    gx[i] = 0.f;
+    xl[i] = xs[row * 16 + i];
+  }
+  mbar_wait_wd(&bar_g[ti & 1], (uint32_t)((ti >> 1) & 1));
+  tc_fence_after();
+  DC_TC_TRACE_TILE(4, 11);
+  if constexpr (MODE == TC_GRAD) {
+    uint32_t gm[16], gc[16];
+    tmem_ld16(tm_lane + L::COL_G + (uint32_t)(ti & 1) * L::N2, gm);
+    tmem_ld16(tm_lane + L::COL_G + (uint32_t)(ti & 1) * L::N2 + 16, gc);
+    tmem_wait_ld();
+#ifdef DC_TC_ENABLE_TRACE
+    if (a.dbg != nullptr && t0 + ti == 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        a.dbg[(size_t)TM * (nch * NC) + row * 32 + c] = __uint_as_float(gm[c]);
+        a.dbg[(size_t)TM * (nch * NC) + row * 32 + 16 + c] = __uint_as_float(gc[c]);
+      }
+    }
+#endif
+    const float csum = __uint_as_float(gm[L::ONES_ROW]) + __uint_as_float(gc[L::ONES_ROW]);  // sum cc w
+#pragma unroll
+    for (int f = 0; f < FM; ++f) {
+      const float gsum = __uint_as_float(gm[f]) + __uint_as_float(gc[f]);              // sum cc w s
+      const float gex = gacc_w[lane * 16 + f - 4 * 32 * 16] + gacc_w[lane * 16 + f];  // column halves 0 + 1
+      gx[f] = a.rc.grad_scale * (fmaf(xl[f], csum, -gsum) * inv_g + gex);
+    }
+  }
+  tc_fence_before();
+  const float score = a.rc.score_scale * ((sc_p[row] + (sc2.lo() + sc2.hi())) * (1.f / 1024.f) +
+                                          (sacc_w[lane - 4 * 32] + sacc_w[lane]));
+  if (ti + 1 < ntile) named_arrive(TCB_ACC, QT);  // the lower half may reset its accumulators for tile ti + 1
+  named_sync(TCB_OWN, TM);  // every owner has read its accumulators: their region becomes `os`
+  if (row < nq) {
+    float* rec = os + row * n_out;
+    rec[0] = score;
+    if constexpr (MODE == TC_GRAD) {
+      const float scale = (a.grad_out != nullptr) ? a.grad_out[b_base + row] : 1.f;
+      if (!has_fk) {
+        for (int f = 0; f < F; ++f) rec[1 + f] = scale * gx[f];
+      } else {
+        float gq[DC_MAX_DOF];
+#pragma unroll
+        for (int i = 0; i < DC_MAX_DOF; ++i) gq[i] = 0.f;
+        if (a.fk.type == DC_FK_PLANAR_CHAIN) {
+          fk_planar_vjp_reg<FM / 2>(a.fk.n_links, xl, gx, gq);  // the BASELINE robot: J^T in registers
+#pragma unroll
+          for (int i = 0; i < FM / 2; ++i)
+            if (i < a.n_in) rec[1 + i] = scale * gq[i];
+        } else {
+          float qv[DC_MAX_DOF];
+          const float* qs = qs_all + buf * TM * L::QS_DOF;
+#pragma unroll
+          for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
+          fk_vjp<float>(a.fk, qv, xl, 1, gx, 1, gq);
+          for (int i = 0; i < a.n_in; ++i) rec[1 + i] = scale * gq[i];
+        }
+      }
+    }
+  }
+  DC_TC_TRACE_TILE(4, 12);
+  named_sync(TCB_OWN, TM);
+  const int otid = tid - TM;  // 0 .. 127
+  if (fused) {
+    // n_bcast > 0: the same block goes to every rank's gathered buffer (peer stores over NVLink) — the all-gather of
+    // the multi-GPU path, overlapped with the other tiles' arithmetic
+    const int n_dst = a.n_bcast > 0 ? a.n_bcast : 1;
+    const size_t off = (size_t)(a.score - (a.n_bcast > 0 ? a.bcast[0] : a.score)) + (size_t)b_base * n_out;
+    const int n_words = nq * n_out;
+    if (a.n_bcast > 0 && (n_words & 3) == 0 && (off & 3) == 0) {
+      // one bulk TMA store of the whole block per destination (shared -> peer global, large NVLink packets, no
+      // thread is held by the transfer); the bases are 16-byte aligned (dc_score_grad_bcast), so `off & 3` decides
+      if (otid == 0) {
+        fence_proxy_async();
+        for (int k = 0; k < n_dst; ++k)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.bcast[k] + off),
+                       "r"(smem_u32(os)), "r"(n_words * 4)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else {
+      for (int k = 0; k < n_dst; ++k) {
+        float* dst = (a.n_bcast > 0 ? a.bcast[k] : a.score) + off;
+        if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          for (int i = otid; i < n_words / 4; i += TM) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
+        } else {
+          for (int i = otid; i < n_words; i += TM) dst[i] = os[i];
+        }
+      }
+    }
+  } else {
+    if (otid < nq) a.score[(size_t)(b_base + otid) * a.score_ld] = os[otid * n_out];
+    if constexpr (MODE == TC_GRAD) {
+      for (int i = otid; i < nq * a.n_in; i += TM) {
+        const int tq = i / a.n_in, c = i - tq * a.n_in;
+        a.grad[(size_t)(b_base + tq) * a.grad_ld + c] = os[tq * n_out + 1 + c];
+      }
+    }
+  }
+  if (a.mirror != nullptr) {
+    float* dst = a.mirror + (size_t)b_base * n_out;
+    const int n_words = nq * n_out;
+    if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      for (int i = otid; i < n_words / 4; i += TM) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
+    } else {
+      for (int i = otid; i < n_words; i += TM) dst[i] = os[i];
+    }
+  }
+  named_sync(TCB_OWN, TM);  // `os` is consumed: the owners' accumulators are reset by the next tile
+  DC_TC_TRACE_TILE(4, 13);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __grid_constant__ TcArgs a) {
   using L = TcLayout;
-  constexpr int NC = L::NC, FM = L::FMAX, QT = L::QTHREADS, TM = L::TM;
+  constexpr int NC = L::NC, QT = L::QTHREADS, TM = L::TM;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -447,11 +821,8 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
   unsigned char* ring1 = smem + L::SM_RING1;
   unsigned char* ring2 = smem + L::SM_RING2;
   unsigned char* a_op = smem + L::SM_A;
-  float* xs_all = reinterpret_cast<float*>(smem + L::SM_XS);     // [2][128][16]
   float* sacc = reinterpret_cast<float*>(smem + L::SM_ACC);      // [8][32]
   float* gacc = sacc + L::QWARPS * 32;                           // [8][32][16]
-  float* os = gacc + 4 * 32 * 16;                                // [128][n_out] over the owners' accumulators
-  float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);     // [2][128][QS_DOF]
   float* sc_p = reinterpret_cast<float*>(smem + L::SM_ROWS);     // [128] score partial of the lower column half
   float* xx_all = sc_p + TM;                                     // [2][128] |x|^2 (negative: out of f16 range)
   uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L::SM_QUEUE);
@@ -595,123 +966,18 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
     uint32_t* queue = queues + warp * L::QCAP;
     float* gacc_w = gacc + warp * 32 * 16;
     float* sacc_w = sacc + warp * 32;
-    const int F = a.n_feat;
-    const int n_out = 1 + (MODE == TC_GRAD ? a.n_in : 0);
-    const bool fused = (MODE == TC_GRAD) ? (a.score_ld == a.grad_ld && a.score_ld == n_out && a.grad == a.score + 1)
-                                         : (a.score_ld == 1);
-    const bool has_fk = a.fk.type != DC_FK_NONE;
-    const float s2max = trailer[0], sa = trailer[3], tc0 = trailer[4], tau = trailer[5], inv_g = trailer[6];
+    const float s2max = trailer[0], tau = trailer[5];
 #ifdef DC_TC_ENABLE_TRACE
     const float inv_tc0 = trailer[9];
 #endif
     const float kq = -a.rc.grad_scale * 0.5f * a.err_coef / a.tol_pair;  // gamma err / tol
     const float4* wrow4 = reinterpret_cast<const float4*>(wsec + hcol * (NC / 2));
 
-    // ---- lower half: configurations of tile ti -> FK -> features, |x|^2, A operand -----------------------------------
-    auto fk_stage = [&](int ti) {
-      const int buf = ti & 1;
-      const long long b_base = (t0 + ti) * TM;
-      const int nq = (int)min((long long)TM, a.batch - b_base);
-      float* xs = xs_all + buf * TM * 16;
-      float* qs = qs_all + buf * TM * L::QS_DOF;
-      const float* src = a.q + (size_t)b_base * a.n_in;
-      const int n_words = nq * a.n_in;
-      float x[FM];
-      float qv[DC_MAX_DOF];
-      if (has_fk) {
-        // coalesced staging of the tile's configurations (also what makes zero-copy reads of pinned host memory efficient)
-        if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-          const float4* s4 = reinterpret_cast<const float4*>(src);
-          for (int i = tid; i < n_words / 4; i += TM) reinterpret_cast<float4*>(qs)[i] = s4[i];
-        } else {
-          for (int i = tid; i < n_words; i += TM) qs[i] = src[i];
-        }
-        named_sync(TCB_LOW, TM);
-#pragma unroll
-        for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (row < nq && i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
-        float xl[DC_MAX_DOF];
-#pragma unroll
-        for (int i = 0; i < DC_MAX_DOF; ++i) xl[i] = 0.f;
-        if (row < nq) fk_forward<float>(a.fk, qv, xl, 1);
-#pragma unroll
-        for (int f = 0; f < FM; ++f) x[f] = (f < F) ? xl[f] : 0.f;
-      } else {
-        // transform=None: the rows ARE the features; staged straight into the feature layout [128][16]
-        for (int i = tid; i < TM * 16; i += TM) xs[i] = 0.f;
-        named_sync(TCB_LOW, TM);
-        for (int i = tid; i < n_words; i += TM) {
-          const int r = i / a.n_in;
-          xs[r * 16 + (i - r * a.n_in)] = src[i];
-        }
-        named_sync(TCB_LOW, TM);
-#pragma unroll
-        for (int f = 0; f < FM; ++f) x[f] = xs[row * 16 + f];
-      }
-      float xx = 0.f, xamax = 0.f;
-#pragma unroll
-      for (int f = 0; f < FM; ++f) {
-        xx = fmaf(x[f], x[f], xx);
-        xamax = fmaxf(xamax, fabsf(x[f]));
-      }
-      {
-        float4* xr = reinterpret_cast<float4*>(xs + row * 16);
-        xr[0] = make_float4(x[0], x[1], x[2], x[3]);
-        xr[1] = make_float4(x[4], x[5], x[6], x[7]);
-        xr[2] = make_float4(x[8], x[9], x[10], x[11]);
-        xr[3] = make_float4(x[12], x[13], 0.f, 0.f);
-      }
-      // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
-      const bool in_range = (sa * xamax < 32768.f) && (tc0 * xx < 32768.f);
-      {
-        float v[L::K1];
-        const float XX = in_range ? tc0 * xx : 0.f;
-#pragma unroll
-        for (int k = 0; k < L::K1; ++k) v[k] = 0.f;
-#pragma unroll
-        for (int f = 0; f < FM; ++f) {
-          const float xsc = in_range ? sa * x[f] : 0.f;
-          const float hi = split_hi(xsc);
-          v[f] = hi;                       // x beta s_h
-          v[16 + f] = (xsc - hi) * 256.f;  // x beta s_h / 256
-          v[32 + f] = hi * (1.f / 256.f);  // x 256 (beta s)_lo
-        }
-        const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
-        v[14] = 1.f;  // x S1   (S = tau (1 + c0 |s|^2), three terms)
-        v[15] = 1.f;  // x S2
-        v[30] = 1.f;  // x S3
-        v[31] = x1;   // x 1
-        v[46] = x2;   // x 1
-        v[47] = x3;   // x 1
-#pragma unroll
-        for (int kc = 0; kc < L::K1 / 8; ++kc) {
-          uint4 pk;
-          pk.x = pack_f16x2(v[8 * kc + 0], v[8 * kc + 1]);
-          pk.y = pack_f16x2(v[8 * kc + 2], v[8 * kc + 3]);
-          pk.z = pack_f16x2(v[8 * kc + 4], v[8 * kc + 5]);
-          pk.w = pack_f16x2(v[8 * kc + 6], v[8 * kc + 7]);
-          reinterpret_cast<uint4*>(a_op)[kc * TM + row] = pk;
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_a);
-      xx_all[buf * TM + row] = in_range ? xx : -1.f;
-#ifdef DC_TC_ENABLE_TRACE
-      if (a.dbg != nullptr && t0 + ti == 0) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) a.dbg[(size_t)TM * (nch * NC) + TM * 32 + row * 16 + c] = c < FM ? x[c] : 0.f;
-      }
-#endif
-      named_arrive(TCB_FK, QT);  // features, |x|^2 (and the staged configurations) of tile ti are visible to the owners
-    };
-
-    if (!owner && ntile > 0) fk_stage(0);
+    if (!owner && ntile > 0) tc_fk_stage(a, 0, tid);
 
     uint32_t g = 0;
     for (int ti = 0; ti < ntile; ++ti) {
       const int buf = ti & 1;
-      const long long b_base = (t0 + ti) * TM;
-      const int nq = (int)min((long long)TM, a.batch - b_base);
-      const float* xs = xs_all + buf * TM * 16;
       if (owner) {
         named_sync(TCB_FK, QT);
       } else if (ti > 0) {
@@ -725,6 +991,11 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         sacc_w[lane] = 0.f;
       }
       __syncwarp();
+#if DC_TC_DEPHASE
+      // The two halves run half a chunk apart: when one half sits in the per-chunk waits (mbarrier, tcgen05.ld / st round
+      // trips) the other is in its arithmetic, instead of both stalling the SM sub-partition at the same moments.
+      if (owner) named_sync(TCB_PHASE, QT);
+#endif
       const float xxq = xx_all[buf * TM + row];
       float thr_c0, thr_c1;
       {
@@ -786,12 +1057,15 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
               if (near) {
                 queue[qcount + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)row << 24) | (uint32_t)(n0 + c);
               }
-              if (lane == 0)  // the row is read when the queue is drained: start pulling it into L1 now
+              if (lane == 0) {  // the rows are read when the queue is drained: start pulling them into L1 now
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(a.table + (size_t)(n0 + c) * a.row_stride));
+                if (a.table_lo != nullptr)
+                  asm volatile("prefetch.global.L1 [%0];" ::"l"(a.table_lo + (size_t)(n0 + c) * a.row_stride));
+              }
               qcount += __popc(bal);
               if (qcount > L::QCAP - 32) {
                 __syncwarp();
-                tc_drain_pairs(a, queue, qcount, xs, gacc_w, sacc_w, lane);
+                tc_drain_pairs(a, qcount, warp, buf);
                 __syncwarp();
                 qcount = 0;
               }
@@ -799,7 +1073,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
           }
           // ---- all pairs: radial profile on the tensor-core T, packed over column pairs ------------------------
           uint32_t outp[16];  // per 8 supports: 4 x f16x2 ch, 4 x f16x2 cl  (GEMM2 K slots 0..7, 8..15)
-          float4 w4[4];
+          float4 w4[4];  // all four loads in flight together (L1 hits, ~35 cycles): issued one by one they are exposed
 #pragma unroll
           for (int c = 0; c < 4; ++c) w4[c] = __ldg(wv4 + bt * 4 + c);
 #pragma unroll
@@ -814,12 +1088,20 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
               // cc = 2^15 u^3 split into two 11-bit f16 terms WITHOUT the conversion unit (F2FP shares the XU pipe with
               // MUFU and was the kernel's binding pipe, profiles/r02e_*): scaling by 2^-112 re-biases the fp32 exponent
               // to f16's, after which `bits >> 13` IS the f16 bit pattern (truncated; f16 denormals included).
+              const int o = (c >> 3) * 8 + ((c & 7) >> 1);
+#if DC_TC_INTPACK
               const P2 cc = pmul_b(pmul(k, u), 0x1p-112f);
               const uint32_t b0 = __float_as_uint(cc.lo()) & 0xffffe000u, b1 = __float_as_uint(cc.hi()) & 0xffffe000u;
               const P2 cl = padd(cc, P2(-__uint_as_float(b0), -__uint_as_float(b1)));  // exact
-              const int o = (c >> 3) * 8 + ((c & 7) >> 1);
               outp[o] = b1 * 8u + (b0 >> 13);  // {ch(c + 1) : ch(c)} as f16x2 (the low 13 bits of b1 are zero)
               outp[o + 4] = __byte_perm(__float_as_uint(cl.lo()) << 3, __float_as_uint(cl.hi()) << 3, 0x7632);
+#else
+              const P2 cc = pmul(k, u);           // 2^15 u^3
+              const P2 ch(split_hi(cc.lo()), split_hi(cc.hi()));
+              const P2 cl = padd(cc, P2(-ch.lo(), -ch.hi()));
+              outp[o] = pack_f16x2(ch.lo(), ch.hi());
+              outp[o + 4] = pack_f16x2(cl.lo(), cl.hi());
+#endif
             }
           }
           if constexpr (MODE == TC_GRAD) tmem_st16(tcol + col0, outp);
@@ -829,6 +1111,9 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         batch(ra, 0);
         tmem_ld16(tcol + 32, ra);  // batch 2 into the first buffer (its values are consumed)
         batch(rc, 1);
+#if DC_TC_DEPHASE
+        if (j == 0 && !owner) named_arrive(TCB_PHASE, QT);  // the owners start their chunk 0 now
+#endif
         tmem_wait_ld();
         batch(ra, 2);
         if (warp == 0) DC_TC_TRACE(12, g);
@@ -841,7 +1126,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
       DC_TC_TRACE_TILE(4, 9);
       if (qcount > 0) {
         __syncwarp();
-        tc_drain_pairs(a, queue, qcount, xs, gacc_w, sacc_w, lane);
+        tc_drain_pairs(a, qcount, warp, buf);
       }
       DC_TC_TRACE_TILE(0, 2);
       DC_TC_TRACE_TILE(4, 10);
@@ -850,111 +1135,12 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         sc_p[row] = sc2.lo() + sc2.hi();
         __threadfence_block();
         named_arrive(TCB_EPI, QT);  // lower half's partial scores and exact terms of tile ti are complete
-        if (ti + 1 < ntile) fk_stage(ti + 1);
+        if (ti + 1 < ntile) tc_fk_stage(a, ti + 1, tid);
         DC_TC_TRACE_TILE(0, 3);
         continue;
       }
 
-      // ---- epilogue (owners): G from TMEM, feature gradient, J_FK^T, records into shared memory ------------------------
-      named_sync(TCB_EPI, QT);
-      float gx[DC_MAX_DOF], xl[DC_MAX_DOF];
-#pragma unroll
-      for (int i = 0; i < DC_MAX_DOF; ++i) {
-        gx[i] = 0.f;
-        xl[i] = xs[row * 16 + i];
-      }
-      mbar_wait_wd(&bar_g[ti & 1], (uint32_t)((ti >> 1) & 1));
-      tc_fence_after();
-      DC_TC_TRACE_TILE(4, 11);
-      if constexpr (MODE == TC_GRAD) {
-        uint32_t gm[16], gc[16];
-        tmem_ld16(tm_lane + L::COL_G + (uint32_t)(ti & 1) * L::N2, gm);
-        tmem_ld16(tm_lane + L::COL_G + (uint32_t)(ti & 1) * L::N2 + 16, gc);
-        tmem_wait_ld();
-#ifdef DC_TC_ENABLE_TRACE
-        if (a.dbg != nullptr && t0 + ti == 0) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            a.dbg[(size_t)TM * (nch * NC) + row * 32 + c] = __uint_as_float(gm[c]);
-            a.dbg[(size_t)TM * (nch * NC) + row * 32 + 16 + c] = __uint_as_float(gc[c]);
-          }
-        }
-#endif
-        const float csum = __uint_as_float(gm[L::ONES_ROW]) + __uint_as_float(gc[L::ONES_ROW]);  // sum cc w
-#pragma unroll
-        for (int f = 0; f < FM; ++f) {
-          const float gsum = __uint_as_float(gm[f]) + __uint_as_float(gc[f]);              // sum cc w s
-          const float gex = gacc_w[lane * 16 + f - 4 * 32 * 16] + gacc_w[lane * 16 + f];  // column halves 0 + 1
-          gx[f] = a.rc.grad_scale * (fmaf(xl[f], csum, -gsum) * inv_g + gex);
-        }
-      }
-      tc_fence_before();
-      const float score = a.rc.score_scale * ((sc_p[row] + (sc2.lo() + sc2.hi())) * (1.f / 1024.f) +
-                                              (sacc_w[lane - 4 * 32] + sacc_w[lane]));
-      if (ti + 1 < ntile) named_arrive(TCB_ACC, QT);  // the lower half may reset its accumulators for tile ti + 1
-      named_sync(TCB_OWN, TM);  // every owner has read its accumulators: their region becomes `os`
-      if (row < nq) {
-        float* rec = os + row * n_out;
-        rec[0] = score;
-        if constexpr (MODE == TC_GRAD) {
-          const float scale = (a.grad_out != nullptr) ? a.grad_out[b_base + row] : 1.f;
-          if (!has_fk) {
-            for (int f = 0; f < F; ++f) rec[1 + f] = scale * gx[f];
-          } else {
-            float gq[DC_MAX_DOF], qv[DC_MAX_DOF];
-            const float* qs = qs_all + buf * TM * L::QS_DOF;
-#pragma unroll
-            for (int i = 0; i < DC_MAX_DOF; ++i) {
-              gq[i] = 0.f;
-              qv[i] = (i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
-            }
-            fk_vjp<float>(a.fk, qv, xl, 1, gx, 1, gq);
-            for (int i = 0; i < a.n_in; ++i) rec[1 + i] = scale * gq[i];
-          }
-        }
-      }
-      DC_TC_TRACE_TILE(4, 12);
-      named_sync(TCB_OWN, TM);
-      const int otid = tid - TM;  // 0 .. 127
-      if (fused) {
-        // n_bcast > 0: the same block goes to every rank's gathered buffer (peer stores over NVLink) — the all-gather of
-        // the multi-GPU path, overlapped with the other tiles' arithmetic
-        const int n_dst = a.n_bcast > 0 ? a.n_bcast : 1;
-        const size_t off = (size_t)(a.score - (a.n_bcast > 0 ? a.bcast[0] : a.score)) + (size_t)b_base * n_out;
-        const int n_words = nq * n_out;
-        if (a.n_bcast > 0 && (n_words & 3) == 0 && (off & 3) == 0) {
-          // one bulk TMA store of the whole block per destination (shared -> peer global, large NVLink packets, no
-          // thread is held by the transfer); the bases are 16-byte aligned (dc_score_grad_bcast), so `off & 3` decides
-          if (otid == 0) {
-            fence_proxy_async();
-            for (int k = 0; k < n_dst; ++k)
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.bcast[k] + off),
-                           "r"(smem_u32(os)), "r"(n_words * 4)
-                           : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
-        } else {
-          for (int k = 0; k < n_dst; ++k) {
-            float* dst = (a.n_bcast > 0 ? a.bcast[k] : a.score) + off;
-            if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-              for (int i = otid; i < n_words / 4; i += TM) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(os)[i];
-            } else {
-              for (int i = otid; i < n_words; i += TM) dst[i] = os[i];
-            }
-          }
-        }
-      } else {
-        if (otid < nq) a.score[(size_t)(b_base + otid) * a.score_ld] = os[otid * n_out];
-        if constexpr (MODE == TC_GRAD) {
-          for (int i = otid; i < nq * a.n_in; i += TM) {
-            const int tq = i / a.n_in, c = i - tq * a.n_in;
-            a.grad[(size_t)(b_base + tq) * a.grad_ld + c] = os[tq * n_out + 1 + c];
-          }
-        }
-      }
-      named_sync(TCB_OWN, TM);  // `os` is consumed: the owners' accumulators are reset by the next tile
-      DC_TC_TRACE_TILE(4, 13);
+      tc_epilogue<MODE>(a, ti, ntile, sc2.lo() + sc2.hi());
     }
     if (tid == TM && a.n_bcast > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // peer stores performed
   }
@@ -975,16 +1161,6 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
       tmem_dealloc(tmem, L::TMEM_COLS);
     }
   }
-}
-
-inline int tc_n_chunks(long long n_sv) { return (int)((n_sv + TcLayout::NC - 1) / TcLayout::NC); }
-inline size_t tc_trailer_offset(long long n_sv) {
-  const size_t nch = (size_t)tc_n_chunks(n_sv);
-  return nch * (TcLayout::B1_BYTES + TcLayout::B2_BYTES) + (nch * TcLayout::NC + ((nch + 3) & ~(size_t)3)) * 4;
-}
-inline size_t tc_blob_bytes(long long n_sv) { return tc_trailer_offset(n_sv) + TcLayout::TRAILER_FLOATS * 4; }
-inline const float* tc_trailer(const void* blob, long long n_sv) {
-  return reinterpret_cast<const float*>(static_cast<const unsigned char*>(blob) + tc_trailer_offset(n_sv));
 }
 
 // Packs S_feat[N,F], w[N] for RQKernel(gamma, p = 2) into `blob` (tc_blob_bytes(N) bytes, 128-byte aligned).

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(512, 1) score_tq_kernel(const __grid_constant_
           T qv[DC_MAX_DOF];
 #pragma unroll
           for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < a.n_in) ? qp[i] : (T)0;
-          fk_forward<T>(a.fk, qv, xs + gtid, QT);
+          fk_features(a.fk, qv, xs + gtid, QT);
         }
       } else {
 #pragma unroll

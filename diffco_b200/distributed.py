@@ -70,7 +70,10 @@ class PeerExchange:
         if self.world > _lib.DC_MAX_PEERS:
             raise RuntimeError(f"at most {_lib.DC_MAX_PEERS} ranks")
         self.rows, self.width, self.device = rows, width, device
-        self.nbytes = self.FLAG_BYTES + 2 * rows * width * 4
+        # each of the two record buffers starts on a 128-byte boundary (the kernel's bulk stores need 16-byte aligned
+        # destinations whatever rows * width is)
+        self.buf_bytes = -(-(rows * width * 4) // 128) * 128
+        self.nbytes = self.FLAG_BYTES + 2 * self.buf_bytes
         self._own, self._opened = C.c_void_p(), []
         # Every rank walks through the SAME sequence of collectives whatever fails locally (allocation, IPC mapping):
         # failures are folded into one consensus at the end, which doubles as the "everyone has mapped every buffer"
@@ -113,11 +116,18 @@ class PeerExchange:
         for r, base in enumerate(bases):
             self.flags.ptr[r] = base
             for k in range(2):
-                self.outs[k].ptr[r] = base + self.FLAG_BYTES + k * rows * width * 4
-        self.views = [torch.as_tensor(_DevicePtr(self._own.value + self.FLAG_BYTES + k * rows * width * 4, (rows, width), "<f4"),
+                self.outs[k].ptr[r] = base + self.FLAG_BYTES + k * self.buf_bytes
+        self.views = [torch.as_tensor(_DevicePtr(self._own.value + self.FLAG_BYTES + k * self.buf_bytes, (rows, width), "<f4"),
                                       device=device) for k in range(2)]
         self.epoch = 0   # barriers so far
         self.steps = 0   # scoring steps so far (selects the buffer)
+
+    def release(self):
+        """Collective: every rank stops using the mapped buffers, THEN they are unmapped and freed (a rank must not free
+        memory a slower peer's kernel may still be storing into)."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self.close()
 
     def close(self):
         for p in getattr(self, "_opened", []):
@@ -133,16 +143,21 @@ class PeerExchange:
         except Exception:
             pass
 
-    def score_and_grad(self, fk, kdesc, sv, q_shard: torch.Tensor) -> Optional[torch.Tensor]:
-        """Scores this rank's shard into every rank's buffer and publishes it.  Returns the (G*b, C+D) view holding the
-        global result, or None when the call is not one the tensor-core kernel takes (caller falls back to NCCL)."""
+    def score_and_grad(self, fk, kdesc, sv, q_shard: torch.Tensor, mirror: Optional[torch.Tensor] = None
+                       ) -> Optional[torch.Tensor]:
+        """Scores this rank's shard into every rank's buffer and publishes it.  ``q_shard`` lives on the device or in pinned
+        host memory (read zero-copy); ``mirror`` (optional, (b, C+D), device or pinned host) receives a copy of this rank's
+        records.  Returns the (G*b, C+D) view holding the global result, or None when the call is not one the tensor-core
+        kernel takes (the answer depends on shapes and options only, so every rank gets the same one and the caller falls
+        back to NCCL on all of them)."""
         b = q_shard.shape[0]
         k = self.steps & 1
         stream = functional._stream_ptr(self.device)
         with torch.cuda.device(self.device):
             st = self.lib.dc_score_grad_bcast(C.byref(fk), C.byref(kdesc), C.byref(sv.desc), q_shard.data_ptr(), b,
-                                              C.byref(self.outs[k]), self.world, self.rank * b, DC_GRAD_SUM, stream)
-            if st == -2:  # DC_ERR_UNSUPPORTED: same answer on every rank (it depends on shapes and options only)
+                                              C.byref(self.outs[k]), self.world, self.rank * b, DC_GRAD_SUM,
+                                              None if mirror is None else mirror.data_ptr(), stream)
+            if st == -2:  # DC_ERR_UNSUPPORTED
                 return None
             _lib.check(st, "dc_score_grad_bcast")
         self.steps += 1
@@ -215,16 +230,30 @@ class ShardedScorer:
     def score_and_grad(self, q_shard: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Every rank passes ITS shard (same row count b on every rank); returns the gathered global result
         (score (G*b, C), grad (G*b, D)) — rank r's rows are [r*b, (r+1)*b)."""
+        rec = self.gathered_records(q_shard)
+        return rec[:, :self.n_class], rec[:, self.n_class:]
+
+    def gathered_records(self, q_shard: torch.Tensor, mirror: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The gathered (G*b, C+D) [score | grad] records of all ranks' shards (a view of the buffer the collective filled).
+        With the fused all-gather ``q_shard`` may be pinned host memory and ``mirror`` receives this rank's records."""
         b = q_shard.shape[0]
-        if self.world > 1 and self._local_fn is None and q_shard.is_cuda and self.dtype == torch.float32:
-            out = self._fused_all_gather(q_shard, b)
+        if self.world > 1 and self._local_fn is None and self.dtype == torch.float32 and (q_shard.is_cuda or q_shard.is_pinned()):
+            out = self._fused_all_gather(q_shard, b, mirror)
             if out is not None:
-                return out[:, :self.n_class], out[:, self.n_class:]
+                return out
+        if not q_shard.is_cuda:
+            if self._q_stage is None or self._q_stage.shape[0] < b:
+                self._q_stage = torch.empty((b, self.dof), dtype=self.dtype, device=self.device)
+            q_dev = self._q_stage[:b]
+            q_dev.copy_(q_shard, non_blocking=True)
+            q_shard = q_dev
         buf = self._buffer(self.world * b)
         self._local(q_shard, buf[self.rank * b:(self.rank + 1) * b])
         if self.world > 1:
             all_gather_rows(buf, b, self.rank, self.group)
-        return buf[:, :self.n_class], buf[:, self.n_class:]
+        if mirror is not None:
+            mirror.copy_(buf[self.rank * b:(self.rank + 1) * b], non_blocking=True)
+        return buf
 
     def align(self) -> None:
         """Stream-ordered rendezvous of all ranks (benchmarks: line the ranks up after untimed work)."""
@@ -236,21 +265,23 @@ class ShardedScorer:
             t = torch.zeros(1, device=self.device)
             dist.all_reduce(t, group=self.group)
 
-    def _fused_all_gather(self, q_shard: torch.Tensor, b: int) -> Optional[torch.Tensor]:
+    def _fused_all_gather(self, q_shard: torch.Tensor, b: int, mirror: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Tensor-core kernel with the all-gather fused into its epilogue (peer stores over NVLink + one flag barrier);
         None when unavailable (DIFFCO_B200_PEER=0, IPC mapping failed, or the call is not a tensor-core one)."""
         if self._peer is False or os.environ.get("DIFFCO_B200_PEER", "1") == "0":
             return None
         if self._peer is None or self._peer_rows != b:
             if self._peer:
-                self._peer.close()
+                self._peer.release()  # collective, like the construction below: every rank sees the same shard size change
             try:  # PeerExchange raises on ALL ranks or on none (its constructor ends with a consensus)
                 self._peer = PeerExchange(self.world * b, self.record_width, self.dtype, self.device, self.group)
                 self._peer_rows = b
             except RuntimeError:
                 self._peer = False
                 return None
-        return self._peer.score_and_grad(self._fk, self._kfun.desc, self._sv, q_shard.detach().contiguous())
+        if mirror is not None and not (mirror.is_cuda or mirror.is_pinned()):
+            return None
+        return self._peer.score_and_grad(self._fk, self._kfun.desc, self._sv, q_shard.detach().contiguous(), mirror)
 
     def score_and_grad_global(self, q_global: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Every rank holds the same global batch (B, D); rank r evaluates rows shard_bounds(B, G, r) and the result for
@@ -275,15 +306,10 @@ class ShardedScorer:
         Returns ``out_host`` once the work is enqueued; the caller synchronises the current stream."""
         if self._local_fn is not None:
             raise RuntimeError("score_and_grad_host needs the CUDA scorer")
-        b = q_host.shape[0]
         if self.world > 1:
-            if self._q_stage is None or self._q_stage.shape[0] < b:
-                self._q_stage = torch.empty((b, self.dof), dtype=self.dtype, device=self.device)
-            qd = self._q_stage[:b]
-            qd.copy_(q_host, non_blocking=True)
-            self.score_and_grad(qd)
-            buf = self._buffer(self.world * b)
-            out_host.copy_(buf[self.rank * b:(self.rank + 1) * b], non_blocking=True)
+            # one launch with pinned buffers (the kernel reads q over PCIe, stores this rank's records to out_host AND to
+            # every peer's gathered buffer); staged copies around the collective otherwise
+            self.gathered_records(q_host, mirror=out_host)
             return out_host
         if self._pipe is None:
             self._pipe = functional.HostPipeline(self.device)

@@ -57,7 +57,7 @@ class SupportSet:
     """
 
     def __init__(self, s_feat: torch.Tensor, weights: torch.Tensor, device: Optional[torch.device] = None,
-                 kernel: Optional[KernelDesc] = None):
+                 kernel: Optional[KernelDesc] = None, s_lo: Optional[torch.Tensor] = None):
         device = device or _require_cuda()
         lib = _lib.load()
         s = s_feat.detach().reshape(s_feat.shape[0], -1)
@@ -99,8 +99,19 @@ class SupportSet:
                 _lib.check(lib.dc_supports_tc_info(ptr, self.n, C.byref(s2), C.byref(valid)), "dc_supports_tc_info")
             if valid.value:
                 self.tc_blob, tc_ptr, s2max, tc_gamma = blob, ptr, s2.value, float(kernel.param)
+        # Optional low parts of the features (fk_forward_split): what float32 rounding dropped from FK(support) — the
+        # tensor-core kernel's exact near-pair path adds them to its differences.
+        self.table_lo = None
+        if s_lo is not None and tc_ptr is not None and dtype == torch.float32:
+            lo = s_lo.detach().reshape(self.n, -1).to(device=device, dtype=dtype).contiguous()
+            if lo.shape != s.shape:
+                raise ValueError(f"s_lo has shape {tuple(lo.shape)}, features have {tuple(s.shape)}")
+            self.table_lo = torch.empty((self.n, row.value), dtype=dtype, device=device)
+            with torch.cuda.device(device):
+                _lib.check(lib.dc_pack_supports_lo(lo.data_ptr(), self.n, self.n_features, self.n_class,
+                                                   self.table_lo.data_ptr(), _stream_ptr(device)), "dc_pack_supports_lo")
         self.desc = Supports(self.table.data_ptr(), self.n, self.n_features, self.n_class, f_pad.value, row.value, code, 0,
-                             tc_ptr, s2max, tc_gamma)
+                             tc_ptr, s2max, tc_gamma, _ptr(self.table_lo))
 
 
 def score_grad(fk: FkDesc, kernel: KernelDesc, sv: SupportSet, q: torch.Tensor, grad_mode: int = DC_GRAD_NONE,
@@ -179,6 +190,19 @@ def fk_forward(fk: FkDesc, q: torch.Tensor) -> torch.Tensor:
             _lib.check(lib.dc_fk_forward(C.byref(fk), q.data_ptr(), q.shape[0], _dtype_code(q.dtype), out.data_ptr(),
                                          _stream_ptr(q.device)), "dc_fk_forward")
     return out
+
+
+def fk_forward_split(fk: FkDesc, q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """float32 features as (hi, lo): FK(q) = hi + lo to ~1e-9, hi == fk_forward(fk, q)."""
+    lib = _lib.load()
+    q = q.detach().to(torch.float32).contiguous()
+    hi = torch.empty((q.shape[0], fk.n_features), dtype=torch.float32, device=q.device)
+    lo = torch.empty_like(hi)
+    if q.shape[0]:
+        with torch.cuda.device(q.device):
+            _lib.check(lib.dc_fk_forward_split(C.byref(fk), q.data_ptr(), q.shape[0], hi.data_ptr(), lo.data_ptr(),
+                                               _stream_ptr(q.device)), "dc_fk_forward_split")
+    return hi, lo
 
 
 def fk_vjp(fk: FkDesc, q: torch.Tensor, g_x: torch.Tensor) -> torch.Tensor:

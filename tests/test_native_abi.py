@@ -119,8 +119,8 @@ def test_tensor_core_peer_and_trajectory_entry_points_validate_arguments(lib):
     assert lib.dc_peer_alloc(0, None, None) == -1 and lib.dc_peer_open(None, None) == -1
     assert lib.dc_peer_close(None) == 0 and lib.dc_peer_free(None) == 0
     fk, kd, sv = _lib.FkDesc(), _lib.KernelDesc(_lib.DC_K_RQ, 2, 10.0), _lib.Supports()
-    assert lib.dc_score_grad_bcast(C.byref(fk), C.byref(kd), C.byref(sv), 64, 8, C.byref(tab), 0, 0, 1, None) == -1
-    assert lib.dc_score_grad_bcast(C.byref(fk), C.byref(kd), C.byref(sv), 64, 8, C.byref(tab), 2, 0, 1, None) == -1  # null outs
+    assert lib.dc_score_grad_bcast(C.byref(fk), C.byref(kd), C.byref(sv), 64, 8, C.byref(tab), 0, 0, 1, None, None) == -1
+    assert lib.dc_score_grad_bcast(C.byref(fk), C.byref(kd), C.byref(sv), 64, 8, C.byref(tab), 2, 0, 1, None, None) == -1  # null outs
     prm = _lib.TrajParams()
     assert lib.dc_traj_step(None, C.byref(prm), 8, 0, None, None, None, None, None, None, None, None, None) == -1
     fk.type, fk.dof, fk.n_points, fk.point_dim, fk.n_links = _lib.DC_FK_PLANAR_CHAIN, 3, 3, 2, 3
