@@ -107,6 +107,11 @@ class TrajParams(C.Structure):
     ]
 
 
+class TrajDense(C.Structure):
+    _fields_ = [("count", C.c_void_p), ("seg_offset", C.c_void_p), ("score", C.c_void_p), ("score_grad", C.c_void_p),
+                ("max_points", C.c_int32), ("reserved", C.c_int32)]
+
+
 DC_OPT_TC_ENABLE, DC_OPT_TC_ERR_COEF, DC_OPT_TC_TOL_PAIR, DC_OPT_TC_MIN_BATCH, DC_OPT_TC_STATS, DC_OPT_PEER_TIMEOUT_S = 1, 2, 3, 4, 5, 6
 KERNEL_NAMES = {0: "lane-split", 1: "thread-per-query", 2: "tensor-core", -1: "none"}
 
@@ -147,6 +152,11 @@ PROTOTYPES = {
                                       C.POINTER(PeerTable), C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_traj_step": (C.c_int, [C.POINTER(FkDesc), C.POINTER(TrajParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dc_traj_dense_path": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dc_traj_step_ex": (C.c_int, [C.POINTER(FkDesc), C.POINTER(TrajParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(TrajDense), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_double, C.c_void_p]),
     "dc_fk_vjp": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

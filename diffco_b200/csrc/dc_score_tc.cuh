@@ -512,6 +512,7 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
   (void)lane;
   (void)warp;
   uint64_t* bar_a = reinterpret_cast<uint64_t*>(smem + L::SM_BAR) + 10;
+  uint64_t* bar_qfull = reinterpret_cast<uint64_t*>(smem + L::SM_BAR) + 13;
   unsigned char* a_op = smem + L::SM_A;
   float* xs_all = reinterpret_cast<float*>(smem + L::SM_XS);
   __half* xlo_all = reinterpret_cast<__half*>(smem + L::SM_XLO);
@@ -535,14 +536,8 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
   float x[FM], xlo[FM];  // features as float32 (hi, lo) pairs of a float64 evaluation (dc_fk.cuh: fk_forward_f32x)
   float qv[DC_MAX_DOF];
   if (has_fk) {
-    // coalesced staging of the tile's configurations (also what makes zero-copy reads of pinned host memory efficient)
-    if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      for (int i = tid; i < n_words / 4; i += TM) reinterpret_cast<float4*>(qs)[i] = s4[i];
-    } else {
-      for (int i = tid; i < n_words; i += TM) qs[i] = src[i];
-    }
-    named_sync(TCB_LOW, TM);
+    // the tile's configurations were staged (coalesced) by the prefetch warp while the previous tile was being scored
+    mbar_wait_wd(bar_qfull + buf, (uint32_t)((ti >> 1) & 1));
 #pragma unroll
     for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (row < nq && i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
     if (a.fk.type == DC_FK_PLANAR_CHAIN) {
@@ -798,6 +793,7 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
       for (int i = otid; i < n_words; i += TM) dst[i] = os[i];
     }
   }
+  if (has_fk) mbar_arrive(reinterpret_cast<uint64_t*>(smem + L::SM_BAR) + 15 + buf);  // qs[buf] may be refilled (tile ti + 2)
   named_sync(TCB_OWN, TM);  // `os` is consumed: the owners' accumulators are reset by the next tile
   DC_TC_TRACE_TILE(4, 13);
 }
@@ -817,6 +813,8 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
   uint64_t* bar_cc = bars + 8;        // [2]   query threads -> GEMM2
   uint64_t* bar_a = bars + 10;        // [1]   A operand written -> GEMM1
   uint64_t* bar_g = bars + 11;        // [2]   last GEMM2 of the tile done -> epilogue
+  uint64_t* bar_qfull = bars + 13;    // [2]   configurations of a tile staged -> FK stage
+  uint64_t* bar_qfree = bars + 15;    // [2]   epilogue done with the staged configurations -> prefetch warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::SM_TMEM_SLOT);
   unsigned char* ring1 = smem + L::SM_RING1;
   unsigned char* ring2 = smem + L::SM_RING2;
@@ -858,6 +856,8 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         mbar_init(&bar_rho[i], 1);
         mbar_init(&bar_cc[i], QT);
         mbar_init(&bar_g[i], 1);
+        mbar_init(&bar_qfull[i], 32);
+        mbar_init(&bar_qfree[i], TM);
       }
       mbar_init(bar_a, TM);
       fence_mbar_init();
@@ -939,6 +939,28 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
                        &bar_b1full[st]);
         }
         __syncwarp();
+      }
+    } else if (warp == L::CTRL_WARP + 3) {
+      // ================= configurations of tile ti -> shared memory (coalesced 16-byte loads), up to two tiles ahead: the
+      // global / PCIe latency (q may be a pinned host buffer, read zero-copy) hides behind the scoring of the earlier tiles
+      if (a.fk.type != DC_FK_NONE) {
+        float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);
+        for (int ti = 0; ti < ntile; ++ti) {
+          const int buf = ti & 1;
+          if (ti >= 2) mbar_wait_wd(&bar_qfree[buf], (uint32_t)(((ti - 2) >> 1) & 1));
+          const long long b_base = (t0 + ti) * TM;
+          const int nq = (int)min((long long)TM, a.batch - b_base);
+          const float* src = a.q + (size_t)b_base * a.n_in;
+          float* qs = qs_all + buf * TM * L::QS_DOF;
+          const int n_words = nq * a.n_in;
+          if ((n_words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            for (int i = lane; i < n_words / 4; i += 32) reinterpret_cast<float4*>(qs)[i] = s4[i];
+          } else {
+            for (int i = lane; i < n_words; i += 32) qs[i] = src[i];
+          }
+          mbar_arrive(&bar_qfull[buf]);  // release: the stores above are visible to whoever observes the phase
+        }
       }
     } else if (warp == L::CTRL_WARP + 2) {
       // ================= GEMM2 operand images: slot gg & 1 is free again once GEMM2(gg - 2) has completed ==============

@@ -241,7 +241,7 @@ class ShardedScorer:
             out = self._fused_all_gather(q_shard, b, mirror)
             if out is not None:
                 return out
-        if not q_shard.is_cuda:
+        if not q_shard.is_cuda and self.device.type == "cuda":
             if self._q_stage is None or self._q_stage.shape[0] < b:
                 self._q_stage = torch.empty((b, self.dof), dtype=self.dtype, device=self.device)
             q_dev = self._q_stage[:b]

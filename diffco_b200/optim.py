@@ -328,6 +328,7 @@ class Weighted(TrajOptimizer):
         self.optimizer_params = options["optimizer_params"]
         self.dense_check = options["dense_check"]
         self.fused = bool(options.get("fused", False))
+        self._fused_cache = None  # (key, GraphedWeightedStep): the captured CUDA graph survives across step() calls
         self._logger = None
 
     def setup_logger(self, logger):

@@ -266,6 +266,32 @@ int dc_traj_step(const dc_fk_desc* fk, const dc_traj_params* params, int64_t n_w
                  const void* score, const void* score_grad, const void* mask, void* exp_avg, void* exp_avg_sq, double* step,
                  void* terms, dc_stream_t stream);
 
+/*
+ * Dense collision checking and the device-side exit test of Weighted.step (diffco/optim.py:709-711,747-752).
+ * dc_traj_dense_path is utils.dense_path (diffco/utils.py:87-102) on the device: per segment ceil(|dq| / max_step) points
+ * q[i] + k max_step dq/|dq|, then the last waypoint, written to dense[max_points][dof] (rows beyond the point count are
+ * filled with the last waypoint, so a scoring launch of the static size max_points is well defined); seg_offset[W]
+ * receives the index of each segment's first point, *count the number of points (-1: more than max_points).
+ * dc_traj_step_ex is dc_traj_step with (a) `dense` != NULL: the collision term is mean(hinge over the dense points) x W
+ * and its gradient is chained through the interpolation to the waypoints (score / score_grad must then be NULL);
+ * (b) `state` != NULL (device int32[2]): state[0] != 0 turns the launch (and dc_traj_dense_path) into a no-op, after
+ * the update state[1] += 1 and state[0] = 1 once the constraint loss is <= exit_constraint — the reference's early
+ * exit, so that a CUDA graph can be replayed several times between host read-backs without overshooting.
+ */
+typedef struct dc_traj_dense {
+  const int32_t* count;
+  const int32_t* seg_offset;
+  const void* score;      /* [max_points]       dc_score_grad of the dense points */
+  const void* score_grad; /* [max_points][dof] */
+  int32_t max_points;
+  int32_t reserved;
+} dc_traj_dense;
+int dc_traj_dense_path(const void* p, int64_t n_waypoints, int32_t dof, int32_t dtype, double max_step, int32_t max_points,
+                       void* dense, int32_t* seg_offset, int32_t* count, const int32_t* state, dc_stream_t stream);
+int dc_traj_step_ex(const dc_fk_desc* fk, const dc_traj_params* params, int64_t n_waypoints, int32_t dtype, void* p,
+                    const void* score, const void* score_grad, const dc_traj_dense* dense, const void* mask, void* exp_avg,
+                    void* exp_avg_sq, double* step, void* terms, int32_t* state, double exit_constraint, dc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

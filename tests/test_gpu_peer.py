@@ -11,7 +11,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, rname="planar7", b=4224):
     import torch.distributed as dist
 
     from diffco_b200 import DiffCo, _lib
@@ -24,15 +24,16 @@ def _worker(rank, world, port, ret):
     try:
         torch.cuda.set_device(0)
         dev = torch.device("cuda", 0)
-        robot, S, W = P.synthetic_model("planar7", 700, 1, seed=77)
+        robot, S, W = P.synthetic_model(rname, 700, 1, seed=77)
         dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine)
         dc.support_points = S.float().to(dev)
         dc.support_transformed = robot.fkine(dc.support_points)
         dc.gains = W[:, 0].float().to(dev)
         scorer = D.ShardedScorer(dc, weights="gains", group=dist.group.WORLD)
         single = D.ShardedScorer(dc, weights="gains")
-        b = 4224  # 33 tiles per rank
         worst = 0.0
+        q_host = torch.empty((b, robot.dof), dtype=torch.float32).pin_memory()
+        out_host = torch.empty((b, 1 + robot.dof), dtype=torch.float32).pin_memory()
         for step in range(5):  # both alternating buffers, several epochs
             q = P.sample_configs(robot, world * b, torch.Generator().manual_seed(100 + step)).float().to(dev)
             s, g = scorer.score_and_grad(q[rank * b:(rank + 1) * b])
@@ -41,12 +42,23 @@ def _worker(rank, world, port, ret):
             s1, g1 = single.score_and_grad(q)
             assert _lib.load().dc_last_score_kernel() == 2
             worst = max(worst, float((s - s1).abs().max() / s1.abs().max()), float((g - g1).abs().max() / g1.abs().max()))
+            # host buffers in / host buffers out with world > 1: ONE launch (pinned q read zero-copy, this rank's records
+            # mirrored to the pinned output) — must equal this rank's rows of the single-process result
+            q_host.copy_(q[rank * b:(rank + 1) * b])
+            out_host.fill_(float("nan"))
+            scorer.score_and_grad_host(q_host, out_host)
+            torch.cuda.synchronize(dev)
+            want = torch.cat([s1, g1], dim=1)[rank * b:(rank + 1) * b].cpu()
+            assert torch.equal(out_host, want), float((out_host - want).abs().max())
         ret[rank] = worst
     finally:
         dist.destroy_process_group()
 
 
-def test_fused_all_gather_two_ranks_one_device(cuda_device):
+@pytest.mark.parametrize("rname,b", [("planar7", 4224), ("se2arm", 4099)])
+def test_fused_all_gather_two_ranks_one_device(rname, b, cuda_device):
+    """planar7: 8-float records, 33 full tiles per rank (bulk-TMA peer stores).  se2arm: 7-float records and a ragged shard, so
+    rank 1's block starts at an address that is NOT 16-byte aligned — the per-thread store path must take over."""
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
@@ -54,7 +66,7 @@ def test_fused_all_gather_two_ranks_one_device(cuda_device):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, rname, b)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

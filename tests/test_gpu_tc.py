@@ -70,12 +70,15 @@ def test_tensor_core_kernel_matches_oracle_and_fp32_kernel(rname, dev, lib):
     es, eg = rel(s, s_ref), rel(g, g_ref)
     es0, eg0 = rel(s0, s_ref), rel(g0, g_ref)
     print(f"{rname}: tensor-core score {es:.2e} grad {eg:.2e} | fp32 kernel score {es0:.2e} grad {eg0:.2e}", flush=True)
-    # se2arm (base translations up to 10 m) sits at 1.08e-5 for BOTH kernels on the near clusters: that is the float32
-    # forward kinematics next to a support vector, not the kernel; the tensor-core path is held to the FP32 path's level
-    gate = 1e-5 if rname != "se2arm" else 2e-5
-    assert es0 <= gate and eg0 <= gate
-    assert es <= gate and eg <= gate and es <= 1.25 * es0 + 1e-6 and eg <= 1.25 * eg0 + 1e-6
-    assert rel(s, s0) <= 1e-5 and rel(g, g0) <= 1e-5
+    # The tensor-core path is held to 1e-5 everywhere: its exact near-pair path works on (hi, lo) feature pairs from the
+    # float64 forward kinematics.  The FP32-pipe kernel sees the float32 features only; with se2arm's base translations
+    # of up to 10 m (ulp 9.5e-7) that alone is ~1.1e-5 of the gradient maximum next to a support vector — the stated
+    # float32-feature limit of that kernel, not a property of this one.
+    gate0 = 1e-5 if rname != "se2arm" else 2e-5
+    assert es0 <= gate0 and eg0 <= gate0
+    assert es <= 1e-5 and eg <= 1e-5
+    assert rel(s, s0) <= gate0 and rel(g, g0) <= gate0
+    gate = 1e-5
     # score-only instantiation and the upstream gradient folded into the launch
     s1, none, which1 = run(lib, robot, kfun, sv, qd, _lib.DC_GRAD_NONE, tc=True)
     assert which1 == which and none is None and rel(s1, s_ref) <= 1e-5

@@ -28,10 +28,10 @@ pytestmark = pytest.mark.gpu
 TC = 2
 N_SEEDS = 50
 BATCH = 8192
-# se2arm: float32 forward kinematics with base translations up to +-10 m rounds the features to 4.8e-7; next to a
-# support vector that alone is 1.1e-5 of the gradient maximum for ANY float32 kernel (the FP32-pipe kernel shows the
-# same figure, tests/test_gpu_tc.py) — a stated deviation, not a property of the tensor-core path.
-GATES = {"planar7": 1e-5, "planar3": 1e-5, "se2arm": 2e-5}
+# One gate for every robot, se2arm (base translations up to +-10 m) included: the tensor-core kernel takes its features from
+# a float64 forward kinematics as float32 (hi, lo) pairs, so close pairs are differenced to ~1e-9.  The FP32-pipe kernel,
+# which sees the rounded features only, is printed beside it: it reaches 1e-5 on exactly these batches.
+GATES = {"planar7": 1e-5, "planar3": 1e-5, "se2arm": 1e-5}
 
 
 @pytest.fixture(scope="module")
