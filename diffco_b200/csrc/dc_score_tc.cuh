@@ -57,12 +57,16 @@ struct TcLayout {
   static constexpr int N2 = 32;    // GEMM2 N: [w s (14), w, 0 | corrections (14), w correction, 0]
   static constexpr int ONES_ROW = 14;
   static constexpr int KS2 = NC / 8;  // GEMM2 instructions per chunk (8 supports x {ch, cl} each)
-  // operand images (bytes).  Global layout: [n_chunks x B1][n_chunks x B2][weights n_chunks x NC f32][chunk max|s|^2,
-  // n_chunks f32 padded to a multiple of 4][trailer].  The weights and chunk maxima are read straight from global memory
-  // (warp-uniform 16-byte loads, L1-resident: 8 KB for 2000 supports), so the query warps never wait for the GEMM2 image.
+  // operand images (bytes).  Global layout: [n_chunks x B1][n_chunks x B2W][trailer]; a B2W record is the GEMM2 image
+  // followed by the chunk's fp32 weights [NC] and its max|s|^2.  (Reading the weights through the L1 instead was
+  // measured: with 2 x 112 KB of shared memory only 28 KB of L1 remain, 15 % of those loads missed and showed up as
+  // the kernel's top stall, profiles/r02o_*.)
   static constexpr int B1_BYTES = NC * K1 * 2;        // [K1/8][NC][8] f16           9216
   static constexpr int B2_STEP_BYTES = N2 * 16 * 2;   // per 8 supports: [2][32][8]  1024
   static constexpr int B2_BYTES = KS2 * B2_STEP_BYTES;  // 12288
+  static constexpr int OFF_W = B2_BYTES;              // fp32 weights [NC], then the chunk's max |s|^2
+  static constexpr int META_S2MAX = NC;               // float index in the weight section
+  static constexpr int B2W_BYTES = B2_BYTES + 512;    // 12800
   // trailer floats: 0 max|s|^2 (bits, atomicMax)  1 max |w| max(1, |s_f|) (bits)  2 max |s_f| (bits)
   //                 3 Sa  4 tau c0  5 tau  6 1/(2^15 Sg)  7 gamma  8 valid (1.0 / 0.0)  9 1/(tau c0)
   static constexpr int TRAILER_FLOATS = 16;
@@ -73,7 +77,7 @@ struct TcLayout {
   static constexpr int TMEM_COLS = 256;
   // near-pair queue entries per warp: large enough that queues are normally drained once, at the end of the tile — a
   // drain in the middle of the chunk loop stalls its warp for ~1500 cycles and, through the chunk barriers, the whole CTA
-  static constexpr int QCAP = 192;
+  static constexpr int QCAP = 160;
   static constexpr int QWARPS = 8;   // query warps: 4 TMEM lane quarters x 2 column halves
   static constexpr int QTHREADS = QWARPS * 32;
   static constexpr int CTRL_WARP = QWARPS;
@@ -84,7 +88,7 @@ struct TcLayout {
   static constexpr int SM_TMEM_SLOT = 192;
   static constexpr int SM_RING1 = 256;
   static constexpr int SM_RING2 = SM_RING1 + RS1 * B1_BYTES;
-  static constexpr int SM_A = SM_RING2 + RS2 * B2_BYTES;    // A [K1/8][128][8] f16
+  static constexpr int SM_A = SM_RING2 + RS2 * B2W_BYTES;   // A [K1/8][128][8] f16
   static constexpr int SM_XS = SM_A + TM * K1 * 2;          // features [2][128][16] f32 (near-pair path, epilogue)
   static constexpr int XLO_SCALE_LOG2 = 22;                 // low parts are kept as f16 of 2^22 lo (|lo| <= ulp(hi) / 2)
   // exact-path accumulators: score [8][32], feature gradient [8][32][16] (non-owner warps first); the owners' half
@@ -93,8 +97,8 @@ struct TcLayout {
   static constexpr int SM_ACC = SM_XLO + 2 * TM * 16 * 2;
   static constexpr int ACC_BYTES = QWARPS * 32 * 4 + QWARPS * 32 * 16 * 4 + 512;
   static constexpr int SM_QS = SM_ACC + ACC_BYTES;          // staged configurations [2][128][QS_DOF]
-  static constexpr int SM_ROWS = SM_QS + 2 * TM * QS_DOF * 4;  // lower-half partial scores [128], |x|^2 [2][128]
-  static constexpr int SM_QUEUE = SM_ROWS + 3 * TM * 4;
+  static constexpr int SM_ROWS = SM_QS + 2 * TM * QS_DOF * 4;
+  static constexpr int SM_QUEUE = SM_ROWS + 5 * TM * 4;   // lower-half partial scores [128], near-threshold line [2][128] x 2
   static constexpr int SM_BYTES = SM_QUEUE + QWARPS * QCAP * 4;
 };
 static_assert(2 * (TcLayout::SM_BYTES + 1024) <= 233472, "two CTAs per SM must fit in 228 KB of shared memory");
@@ -103,7 +107,7 @@ static_assert(TcLayout::TM * (DC_MAX_DOF + 1) * 4 <= 4 * 32 * 16 * 4 + 512, "out
 struct TcArgs {
   dc_fk_desc fk;
   RadialConsts<float> rc;
-  const unsigned char* blob;  // [n_chunks x B1][n_chunks x B2][weights][chunk max|s|^2][trailer]
+  const unsigned char* blob;  // [n_chunks x B1][n_chunks x B2W][trailer]
   const float* table;         // packed [-s | w] rows (dc_pack_supports), for the exact near-pair path
   const float* table_lo;      // optional: low parts -(s - fl32(s)) in the same row layout (dc_pack_supports_lo)
   const float* q;
@@ -260,8 +264,7 @@ __device__ __forceinline__ float pow2_floor(float v) { return __uint_as_float(__
 
 __host__ __device__ inline int tc_n_chunks(long long n_sv) { return (int)((n_sv + TcLayout::NC - 1) / TcLayout::NC); }
 __host__ __device__ inline size_t tc_trailer_offset(long long n_sv) {
-  const size_t nch = (size_t)tc_n_chunks(n_sv);
-  return nch * (TcLayout::B1_BYTES + TcLayout::B2_BYTES) + (nch * TcLayout::NC + ((nch + 3) & ~(size_t)3)) * 4;
+  return (size_t)tc_n_chunks(n_sv) * (TcLayout::B1_BYTES + TcLayout::B2W_BYTES);
 }
 __host__ __device__ inline size_t tc_blob_bytes(long long n_sv) { return tc_trailer_offset(n_sv) + TcLayout::TRAILER_FLOATS * 4; }
 __host__ __device__ inline const float* tc_trailer(const void* blob, long long n_sv) {
@@ -320,9 +323,7 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_chunks * L::NC) return;
   unsigned char* blob2 = blob + (size_t)n_chunks * L::B1_BYTES;
-  float* wsec = reinterpret_cast<float*>(blob2 + (size_t)n_chunks * L::B2_BYTES);  // [n_chunks * NC]
-  float* s2sec = wsec + (size_t)n_chunks * L::NC;                                   // [round_up(n_chunks, 4)]
-  float* trailer = s2sec + ((n_chunks + 3) & ~3);
+  float* trailer = reinterpret_cast<float*>(blob2 + (size_t)n_chunks * L::B2W_BYTES);
   const TcScales sc = tc_scales(trailer, gamma);
   if (idx == 0) {
     trailer[3] = sc.sa;
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
 #pragma unroll
   for (int k = 0; k < 16; ++k) mainv[k] = corrv[k] = 0.f;
   float wv = 0.f;
+  float* w_sec = reinterpret_cast<float*>(blob2 + (size_t)j * L::B2W_BYTES + L::OFF_W);
   if (idx < n) {
     wv = w[idx];
     const float gw = sc.sg * wv;  // exact (power of two)
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
     const float gh = split_hi(gw);
     mainv[L::ONES_ROW] = gh;
     corrv[L::ONES_ROW] = gw - gh;
-    atomicMax(reinterpret_cast<int*>(s2sec) + j, __float_as_int(ss));
+    atomicMax(reinterpret_cast<int*>(w_sec) + L::META_S2MAX, __float_as_int(ss));
   } else {
     b1[14] = 32768.f;  // padding rows: T >= 2^15, never near; weight 0 removes them from every sum
   }
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
 #pragma unroll
   for (int k = 0; k < L::K1; ++k) b1p[(k >> 3) * (L::NC * 8) + r * 8 + (k & 7)] = __float2half_rn(b1[k]);
   // GEMM2 image of the 8-support step ks = r / 8: K slot i = r % 8 multiplies ch of support r, slot 8 + i its cl
-  __half* b2p = reinterpret_cast<__half*>(blob2 + (size_t)j * L::B2_BYTES + (r >> 3) * L::B2_STEP_BYTES);
+  __half* b2p = reinterpret_cast<__half*>(blob2 + (size_t)j * L::B2W_BYTES + (r >> 3) * L::B2_STEP_BYTES);
   const int i = r & 7;
 #pragma unroll
   for (int f = 0; f < 16; ++f) {
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
     b2p[0 * (L::N2 * 8) + (16 + f) * 8 + i] = __float2half_rn(corrv[f]);  // slot i,     row 16 + f: low parts
     b2p[1 * (L::N2 * 8) + (16 + f) * 8 + i] = __float2half_rn(0.f);
   }
-  wsec[idx] = wv;
+  w_sec[r] = wv;
 }
 
 #ifdef DC_TC_ENABLE_TRACE
@@ -517,7 +519,7 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
   float* xs_all = reinterpret_cast<float*>(smem + L::SM_XS);
   __half* xlo_all = reinterpret_cast<__half*>(smem + L::SM_XLO);
   float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);
-  float* xx_all = reinterpret_cast<float*>(smem + L::SM_ROWS) + TM;
+  float2* thr_all = reinterpret_cast<float2*>(smem + L::SM_ROWS + TM * 4);
   const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
 #ifdef DC_TC_ENABLE_TRACE
   const int nch = a.n_chunks;
@@ -633,7 +635,18 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
   }
   fence_proxy_async();
   mbar_arrive(bar_a);
-  xx_all[buf * TM + row] = in_range ? xx : -1.f;
+  {
+    // near threshold of this query on T as a line in the chunk's max|s|^2: pairs with 1 + c0 rho < (gamma drho / tol)^(1/3),
+    // drho = err (|x|^2 + max_chunk |s|^2), are recomputed exactly.  The cube root is bounded from above by its tangent at the
+    // largest chunk maximum (concave function): exact for the widest chunk, conservative for the others, one FFMA per chunk.
+    const float s2max = trailer[0], tau = trailer[5];
+    const float kq = -a.rc.grad_scale * 0.5f * a.err_coef / a.tol_pair;  // gamma err / tol
+    const float base = fmaxf(kq * (xx + s2max), 1.f);
+    const float cr = cbrtf(base);
+    const float c1 = tau * 1.001f * kq / (3.f * cr * cr);
+    const float c0 = in_range ? tau * 1.001f * cr - c1 * s2max : 3.0e38f;  // out-of-range rows: every pair is "near"
+    thr_all[buf * TM + row] = make_float2(c0, c1);
+  }
 #ifdef DC_TC_ENABLE_TRACE
   if (a.dbg != nullptr && t0 + ti == 0) {
 #pragma unroll
@@ -822,7 +835,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
   float* sacc = reinterpret_cast<float*>(smem + L::SM_ACC);      // [8][32]
   float* gacc = sacc + L::QWARPS * 32;                           // [8][32][16]
   float* sc_p = reinterpret_cast<float*>(smem + L::SM_ROWS);     // [128] score partial of the lower column half
-  float* xx_all = sc_p + TM;                                     // [2][128] |x|^2 (negative: out of f16 range)
+  const float2* thr_all = reinterpret_cast<const float2*>(sc_p + TM);  // [2][128] near-threshold line (c0, c1) of each query
   uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L::SM_QUEUE);
 
   const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
@@ -843,9 +856,6 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
   const uint32_t total = (uint32_t)ntile * (uint32_t)nch;  // < 2^31 (checked by launch_score_tc)
   const unsigned char* blob1 = a.blob;
   const unsigned char* blob2 = a.blob + (size_t)nch * L::B1_BYTES;
-  const float* wsec = reinterpret_cast<const float*>(blob2 + (size_t)nch * L::B2_BYTES);
-  const float* s2sec = wsec + (size_t)nch * NC;
-  const float* trailer = s2sec + ((nch + 3) & ~3);
 
   if (warp == L::CTRL_WARP) {
     if (lane == 0) {
@@ -904,13 +914,13 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         if (nch > 1) gemm1(g + 1);
         for (int j = 0; j < nch; ++j, ++g) {
           const int st = (int)(g & 1);
-          if constexpr (MODE == TC_GRAD) mbar_wait_wd(&bar_b2full[st], (uint32_t)((g >> 1) & 1));
+          mbar_wait_wd(&bar_b2full[st], (uint32_t)((g >> 1) & 1));
           mbar_wait_wd(&bar_cc[st], (uint32_t)((g >> 1) & 1));
           tc_fence_after();
           DC_TC_TRACE(3, g);
           if (elect_one()) {
             if constexpr (MODE == TC_GRAD) {
-              const uint32_t b_s = smem_u32(ring2 + (size_t)st * L::B2_BYTES);
+              const uint32_t b_s = smem_u32(ring2 + (size_t)st * L::B2W_BYTES);
               const uint32_t cc = tmem + st * L::COL_STAGE;
               const uint32_t d = tmem + L::COL_G + (uint32_t)(ti & 1) * L::N2;
 #pragma unroll
@@ -963,18 +973,17 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         }
       }
     } else if (warp == L::CTRL_WARP + 2) {
-      // ================= GEMM2 operand images: slot gg & 1 is free again once GEMM2(gg - 2) has completed ==============
-      if constexpr (MODE == TC_GRAD) {
-        for (uint32_t gg = 0; gg < total; ++gg) {
-          const int st = (int)(gg & 1);
-          if (gg >= 2) mbar_wait_wd(&bar_b2free[st], (uint32_t)(((gg - 2) >> 1) & 1));
-          if (elect_one()) {
-            mbar_expect_tx(&bar_b2full[st], L::B2_BYTES);
-            tma_bulk_g2s(ring2 + (size_t)st * L::B2_BYTES, blob2 + (size_t)(gg % (uint32_t)nch) * L::B2_BYTES, L::B2_BYTES,
-                         &bar_b2full[st]);
-          }
-          __syncwarp();
+      // ================= GEMM2 operand images + weights: slot gg & 1 is free again once GEMM2(gg - 2) has completed (the
+      // query warps read the weights of chunk gg - 2 before they arrive on bar_cc, which GEMM2(gg - 2) waits for) =============
+      for (uint32_t gg = 0; gg < total; ++gg) {
+        const int st = (int)(gg & 1);
+        if (gg >= 2) mbar_wait_wd(&bar_b2free[st], (uint32_t)(((gg - 2) >> 1) & 1));
+        if (elect_one()) {
+          mbar_expect_tx(&bar_b2full[st], L::B2W_BYTES);
+          tma_bulk_g2s(ring2 + (size_t)st * L::B2W_BYTES, blob2 + (size_t)(gg % (uint32_t)nch) * L::B2W_BYTES, L::B2W_BYTES,
+                       &bar_b2full[st]);
         }
+        __syncwarp();
       }
     }
   } else {
@@ -988,12 +997,10 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
     uint32_t* queue = queues + warp * L::QCAP;
     float* gacc_w = gacc + warp * 32 * 16;
     float* sacc_w = sacc + warp * 32;
-    const float s2max = trailer[0], tau = trailer[5];
 #ifdef DC_TC_ENABLE_TRACE
-    const float inv_tc0 = trailer[9];
+    const float* trailer = tc_trailer(a.blob, a.n_sv);
+    const float tau = trailer[5], inv_tc0 = trailer[9];
 #endif
-    const float kq = -a.rc.grad_scale * 0.5f * a.err_coef / a.tol_pair;  // gamma err / tol
-    const float4* wrow4 = reinterpret_cast<const float4*>(wsec + hcol * (NC / 2));
 
     if (!owner && ntile > 0) tc_fk_stage(a, 0, tid);
 
@@ -1018,22 +1025,17 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
       // trips) the other is in its arithmetic, instead of both stalling the SM sub-partition at the same moments.
       if (owner) named_sync(TCB_PHASE, QT);
 #endif
-      const float xxq = xx_all[buf * TM + row];
-      float thr_c0, thr_c1;
-      {
-        const float base = fmaxf(kq * (fmaxf(xxq, 0.f) + s2max), 1.f);
-        const float cr = cbrtf(base);
-        thr_c1 = tau * 1.001f * kq / (3.f * cr * cr);
-        thr_c0 = (xxq >= 0.f) ? tau * 1.001f * cr - thr_c1 * s2max : 3.0e38f;  // out-of-range rows: every pair is "near"
-      }
 
       P2 sc2(0.f, 0.f);
       int qcount = 0;
       for (int j = 0; j < nch; ++j, ++g) {
         const int st = (int)(g & 1);
-        const float4* wv4 = wrow4 + j * (NC / 4);  // this chunk's weights, warp-uniform 16-byte loads (L1)
+        // this chunk's weights (warp-uniform LDS.128 broadcasts) and max|s|^2 ride with the GEMM2 image
+        const float* wsm = reinterpret_cast<const float*>(ring2 + (size_t)st * L::B2W_BYTES + L::OFF_W);
+        const float4* wv4 = reinterpret_cast<const float4*>(wsm + hcol * (NC / 2));
         if (warp == 0) DC_TC_TRACE(8, g);
-        const float s2j = __ldg(s2sec + j);
+        mbar_wait_wd(&bar_b2full[st], (uint32_t)((g >> 1) & 1));
+        const float s2j = wsm[L::META_S2MAX];
         mbar_wait_wd(&bar_rho[st], (uint32_t)((g >> 1) & 1));
         tc_fence_after();
         if (warp == 0) DC_TC_TRACE(10, g);
@@ -1042,10 +1044,10 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         uint32_t ra[16], rc[16];
         tmem_ld16(tcol, ra);
         tmem_ld16(tcol + 16, rc);
-        // near threshold of this (query, chunk) on T: pairs with 1 + c0 rho < (gamma drho / tol)^(1/3), drho = err (|x|^2 +
-        // max_chunk |s|^2), are recomputed exactly.  The cube root is bounded from above by its tangent at the largest chunk
-        // maximum (concave function): one FFMA per chunk, exact for the widest chunk, conservative for the others.
-        const float thr = fmaf(thr_c1, s2j, thr_c0);
+        // near threshold of this (query, chunk) on T (the line was set up by tc_fk_stage; kept in shared memory, not in
+        // registers: the chunk loop has none to spare, and a spilled register would compete with the weights for the L1)
+        const float2 tl = thr_all[buf * TM + row];
+        const float thr = fmaf(tl.y, s2j, tl.x);
         auto batch = [&](uint32_t* rb, const int bt) {
           const int col0 = bt * 16;
 #ifdef DC_TC_ENABLE_TRACE
@@ -1095,9 +1097,9 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
           }
           // ---- all pairs: radial profile on the tensor-core T, packed over column pairs ------------------------
           uint32_t outp[16];  // per 8 supports: 4 x f16x2 ch, 4 x f16x2 cl  (GEMM2 K slots 0..7, 8..15)
-          float4 w4[4];  // all four loads in flight together (L1 hits, ~35 cycles): issued one by one they are exposed
+          float4 w4[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) w4[c] = __ldg(wv4 + bt * 4 + c);
+          for (int c = 0; c < 4; ++c) w4[c] = wv4[bt * 4 + c];
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
             const float2 w2 = (c & 2) ? make_float2(w4[c >> 2].z, w4[c >> 2].w) : make_float2(w4[c >> 2].x, w4[c >> 2].y);

@@ -104,8 +104,21 @@ def test_weighted_step_graphed_matches_autograd_path(problem):
     assert P.rel_to_max(fused.x, ref.x) <= 1e-9
     for a, b in zip(fused.misc["path_history"], ref.misc["path_history"]):
         assert P.rel_to_max(a, b) <= 1e-9
-    with pytest.raises(ValueError):
-        OPT.Weighted(robot, dc, dict(options, fused=True, dense_check=True)).step(init.clone())
+    # dense collision checking on the graphed step (device-side dense_path) against the autograd step with utils.dense_path
+    ref_d = OPT.Weighted(robot, dc, dict(options, dense_check=True)).step(init.clone(), mask=mask)
+    opt_d = OPT.Weighted(robot, dc, dict(options, fused=True, dense_check=True))
+    fused_d = opt_d.step(init.clone(), mask=mask)
+    assert len(fused_d.misc["path_history"]) == len(ref_d.misc["path_history"])
+    assert P.rel_to_max(fused_d.x, ref_d.x) <= 1e-9
+    # a second call reuses the captured graph (no re-capture) and gives the same answer; without history the exit state is
+    # read back only every few iterations and must stop at exactly the same iterate
+    stepper = opt_d._fused_cache[1]
+    again = opt_d.step(init.clone(), mask=mask)
+    assert opt_d._fused_cache[1] is stepper and torch.equal(again.x, fused_d.x)
+    lazy = OPT.Weighted(robot, dc, dict(options, fused=True, dense_check=True, history=False)).step(init.clone(), mask=mask)
+    assert torch.equal(lazy.x, fused_d.x)
+    with pytest.raises(RuntimeError):  # more interpolation points than the static bound
+        OPT.Weighted(robot, dc, dict(options, fused=True, dense_check=True, max_dense_points=13, max_speed=0.01)).step(init.clone())
 
 
 def test_weighted_step_graphed_cfg4_256_waypoints():
@@ -154,7 +167,7 @@ def test_adam_traj_optimize_graphed_matches_autograd_and_reference(problem):
         OPT.adam_traj_optimize(robot, lambda q: dc.poly_score(q), start, target, dict(opts, init_solution=init.clone(), fused=True))
 
 
-@pytest.mark.parametrize("mode", ["autograd", "autograd_dense", "graphed"])
+@pytest.mark.parametrize("mode", ["autograd", "autograd_dense", "graphed", "graphed_dense"])
 def test_weighted_step_matches_the_reference_record(mode, cuda_device):
     """Weighted.step on the CUDA path against the waypoints the UNMODIFIED reference's Weighted.step produced
     (tests/golden/weighted.npz: Baxter arm, float64, 25 Adam iterations, with and without dense_check)."""
@@ -168,12 +181,12 @@ def test_weighted_step_matches_the_reference_record(mode, cuda_device):
     dc.train(T64(g["X"]), T64(g["y"]), max_iteration=len(g["X"]))
     assert dc.support_index.tolist() == g["idx"].tolist()
     dc.fit_poly(K.Polyharmonic(1, 1.0), target="label")
-    dense = mode == "autograd_dense"
+    dense = mode.endswith("_dense")
     cw, mmw, jlw = (float(v) for v in g["weights"])
     options = {"n_waypoints": 12, "maxiter": int(g["maxiter"]), "history": True, "max_move_weight": mmw, "collision_weight": cw,
                "joint_limit_weight": jlw, "safety_bias": float(g["safety_bias"]), "max_speed": float(g["max_speed"]),
                "optimizer": torch.optim.Adam, "optimizer_params": {"lr": float(g["lr"])}, "dense_check": dense,
-               "fused": mode == "graphed"}
+               "fused": mode.startswith("graphed")}
     res = OPT.Weighted(robot, dc, options).step(T64(g["init"]), mask=torch.from_numpy(g["mask"]))
     assert len(res.misc["path_history"]) == int(g[f"steps_dense{int(dense)}"])
     assert P.rel_to_max(res.x, T64(g[f"x_dense{int(dense)}"])) <= 1e-6

@@ -90,8 +90,8 @@ def test_tensor_core_peer_and_trajectory_entry_points_validate_arguments(lib):
 
     n = C.c_int64()
     assert lib.dc_supports_tc_bytes(2000, 14, 1, _lib.DC_F32, C.byref(n)) == 0
-    # 21 chunks of 96 supports: GEMM1 + GEMM2 images, fp32 weights, chunk maxima (padded to 4), trailer
-    assert n.value == 21 * (9216 + 12288) + (21 * 96 + 24) * 4 + 64
+    # 21 chunks of 96 supports: GEMM1 image, GEMM2 image + fp32 weights + chunk maximum, trailer
+    assert n.value == 21 * (9216 + 12800) + 64
     assert lib.dc_supports_tc_bytes(2000, 15, 1, _lib.DC_F32, C.byref(n)) == -2   # F > 14
     assert lib.dc_supports_tc_bytes(2000, 14, 4, _lib.DC_F32, C.byref(n)) == -2   # multi-class
     assert lib.dc_supports_tc_bytes(2000, 14, 1, _lib.DC_F64, C.byref(n)) == -2   # float64
