@@ -43,6 +43,10 @@
 #ifndef DC_TC_INTPACK
 #define DC_TC_INTPACK 0   // 1: f16 operand words built with integer ops instead of F2FP (frees the XU pipe): 105.7 us vs 92.9 us
 #endif
+#ifndef DC_TC_PREFETCH
+#define DC_TC_PREFETCH 0  // 1: the first two tcgen05.ld of chunk g + 1 are issued at the end of chunk g (before its st-wait /
+#endif                    //    arrive / loop top): 99.8 us vs 95.2 us — the two buffers stay live across the loop edge and
+                          //    ptxas spills (112 bytes) what it saves in latency (profiles/r02q_variants.txt)
 #ifndef DC_TC_DEPHASE
 #define DC_TC_DEPHASE 0   // 1: the owner half starts each tile half a chunk behind the lower half: 93.6 us vs 92.9 us
 #endif
@@ -1028,6 +1032,8 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
 
       P2 sc2(0.f, 0.f);
       int qcount = 0;
+      // two register buffers of 16 columns: the load of batch b + 1 is in flight while batch b is processed
+      uint32_t ra[16], rc[16];
       for (int j = 0; j < nch; ++j, ++g) {
         const int st = (int)(g & 1);
         // this chunk's weights (warp-uniform LDS.128 broadcasts) and max|s|^2 ride with the GEMM2 image
@@ -1036,14 +1042,14 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         if (warp == 0) DC_TC_TRACE(8, g);
         mbar_wait_wd(&bar_b2full[st], (uint32_t)((g >> 1) & 1));
         const float s2j = wsm[L::META_S2MAX];
-        mbar_wait_wd(&bar_rho[st], (uint32_t)((g >> 1) & 1));
-        tc_fence_after();
-        if (warp == 0) DC_TC_TRACE(10, g);
         const uint32_t tcol = tm_lane + st * L::COL_STAGE + hcol * (NC / 2);
-        // two register buffers of 16 columns: the load of batch b + 1 is in flight while batch b is processed
-        uint32_t ra[16], rc[16];
-        tmem_ld16(tcol, ra);
-        tmem_ld16(tcol + 16, rc);
+        if (!DC_TC_PREFETCH || j == 0) {  // (otherwise issued at the end of the previous chunk)
+          mbar_wait_wd(&bar_rho[st], (uint32_t)((g >> 1) & 1));
+          tc_fence_after();
+          tmem_ld16(tcol, ra);
+          tmem_ld16(tcol + 16, rc);
+        }
+        if (warp == 0) DC_TC_TRACE(10, g);
         // near threshold of this (query, chunk) on T (the line was set up by tc_fk_stage; kept in shared memory, not in
         // registers: the chunk loop has none to spare, and a spilled register would compete with the weights for the L1)
         const float2 tl = thr_all[buf * TM + row];
@@ -1140,6 +1146,17 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
 #endif
         tmem_wait_ld();
         batch(ra, 2);
+#if DC_TC_PREFETCH
+        if (j + 1 < nch) {
+          // T of chunk g + 1 (other stage) was issued two chunks ago and is normally complete: start pulling its first 32
+          // columns now; the loads land while this chunk's stores drain and the arrive / loop top execute
+          mbar_wait_wd(&bar_rho[st ^ 1], (uint32_t)(((g + 1) >> 1) & 1));
+          tc_fence_after();
+          const uint32_t tnext = tm_lane + (st ^ 1) * L::COL_STAGE + hcol * (NC / 2);
+          tmem_ld16(tnext, ra);
+          tmem_ld16(tnext + 16, rc);
+        }
+#endif
         if (warp == 0) DC_TC_TRACE(12, g);
         if constexpr (MODE == TC_GRAD) tmem_wait_st();
         tc_fence_before();

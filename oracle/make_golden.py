@@ -299,13 +299,95 @@ def gen_weighted(ns):
     np.savez_compressed(os.path.join(OUT, "weighted.npz"), **out)
 
 
+def gen_checkers(ns):
+    """The reference's high-level checker (diffco/collision_checkers.py: ForwardKinematicsDiffCo.fit / update-style refit /
+    verify / collision_score) on a 7-link planar arm with a synthetic ground truth (circle obstacles).  The module's
+    geometry back ends (yourdfpy / trimesh / python-fcl / cuRobo / ROS) are stubbed: with an injected gt_check_func and a
+    robot object that provides the members the checker touches, none of them is reached."""
+    import importlib
+    import sys
+    import types
+
+    M = ns.model
+    ci = types.ModuleType("diffco.collision_interfaces")
+    for name in ("RobotInterfaceBase", "URDFRobot", "MultiURDFRobot", "ROSRobotEnv", "CuRoboRobot", "CuRoboCollisionWorldEnv",
+                 "ShapeEnv", "PCDEnv"):
+        setattr(ci, name, type(name, (), {}))
+    ci.robot_description_folder = ""
+    sys.modules["diffco.collision_interfaces"] = ci
+    pkg = sys.modules["diffco"]
+    pkg.collision_interfaces, pkg.model, pkg.kernel = ci, ns.model, ns.kernel
+    cc = importlib.import_module("diffco.collision_checkers")
+
+    planar = M.RevolutePlanarRobot(1.0, 0.3, dof=7)
+
+    class Link:
+        def __init__(self, name):
+            self.name = name
+
+        def joint_trans(self):
+            return torch.ones(3)
+
+    class FakeRobot(ci.RobotInterfaceBase):
+        """What ForwardKinematicsDiffCo touches of a URDFRobot: _bodies, _n_dofs, joint_limits, rand_configs,
+        compute_forward_kinematics_all_links (link name -> [(position (B, 3), rotation)])."""
+
+        def __init__(self):
+            self._bodies = [Link(f"l{i}") for i in range(7)]
+            self._n_dofs = 7
+            self.joint_limits = planar.limits.double()
+            self.gen = torch.Generator().manual_seed(99)
+
+        def rand_configs(self, n):
+            lo, hi = self.joint_limits[:, 0], self.joint_limits[:, 1]
+            return torch.rand(n, 7, generator=self.gen, dtype=torch.float64) * (hi - lo) + lo
+
+        def compute_forward_kinematics_all_links(self, q, return_collision=False):
+            pts = planar.fkine(q)  # (B, 7, 2)
+            pos = torch.cat([pts, torch.zeros_like(pts[..., :1])], dim=-1)
+            return {f"l{i}": [(pos[:, i], None)] for i in range(7)}
+
+        def collision(self, q, other=None):
+            raise AssertionError("the ground truth is injected")
+
+    def gt(q):
+        return (_circle_labels(planar.fkine(q)) > 0).to(q.dtype)
+
+    g = torch.Generator().manual_seed(31)
+    lim = planar.limits.double()
+    X = torch.rand(900, 7, generator=g, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+    chk = cc.ForwardKinematicsDiffCo(robot=FakeRobot(), gt_check_func=gt, device="cpu")
+    torch.manual_seed(5)
+    acc = chk.fit(q=X.clone(), verify_ratio=0.2)
+    dc = chk.perceptron
+    out = {"X": _np(X), "limits": _np(lim), "fit_rates": np.array([float(v) for v in acc]), "fit_bias": _np(chk.safety_bias),
+           "fit_support_points": _np(dc.support_points), "fit_nodes": _np(dc.rbf_nodes), "fit_q_verify": _np(chk.q_verify)}
+    Q = torch.rand(64, 7, generator=g, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+    out["Q"] = _np(Q)
+    out["fit_collision_score"] = _np(chk.collision_score(Q.reshape(4, 16, 7)))
+    out["fit_collision_score_links"] = _np(chk.collision_score(q_link_pos=chk.tensorized_fkine(Q)))  # (B, 3, L): the layout of support_transformed
+    # active-learning refit (update() builds q and exist_mask from the RNG; the same refit with explicit inputs):
+    novel = torch.rand(200, 7, generator=g, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+    Xu = torch.cat([novel, dc.support_points], dim=0)
+    exist = torch.zeros(len(Xu), dtype=torch.bool)
+    exist[-len(dc.support_points):] = True
+    chk.fit(Xu.clone(), update=True, exist_mask=exist, verify_ratio=0)  # q_verify = robot.rand_configs(100)
+    out.update({"upd_X": _np(Xu), "upd_exist": _np(exist), "upd_support_points": _np(dc.support_points),
+                "upd_nodes": _np(dc.rbf_nodes), "upd_bias": _np(chk.safety_bias),
+                "upd_q_verify": _np(FakeRobot().rand_configs(100)),  # the first draw of a fresh generator: what fit() consumed
+                "upd_collision_score": _np(chk.collision_score(Q))})
+    ver = chk.verify(q_verify=Q)
+    out["upd_verify_rates"] = np.array([float(v) for v in ver])
+    np.savez_compressed(os.path.join(OUT, "checkers.npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(4)
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load_legacy()
     only = sys.argv[1:]
-    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay, gen_weighted):
+    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay, gen_weighted, gen_checkers):
         if only and fn.__name__ not in only:
             continue
         fn(ns)
