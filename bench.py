@@ -507,6 +507,7 @@ def run_extras(args, torch, dist, lib, dev, rank, world, group, scorer, checker,
     if world == 1:
         cfgs["cfg3"] = bench_cfg3(torch, lib, dev, timed, hbm_peak)
         cfgs["cfg4"] = bench_cfg4(torch, dev)
+        cfgs["fit"] = bench_fit(torch, dev)
         # ---- the reference's own ATen code on this GPU (courtesy row: fused vs unfused on identical silicon) --------------
         try:
             run = _reference_fn(S, w, torch.float32, device=dev)
@@ -606,6 +607,48 @@ def bench_cfg4(torch, dev):
                         "Weighted.step Adam loop", "value": 1e6 * t_graph, "unit": "us/step (CUDA-graph replay: dc_score_grad + dc_traj_step)",
             "higher_is_better": False, "steps": steps, "autograd_step_us": 1e6 * t_auto,
             "note": "wall clock over the whole Weighted.step call (host loop included); second call, graph cached"}
+
+
+def bench_fit(torch, dev):
+    """ForwardKinematicsDiffCo.fit at the size of the reference's tutorial (Panda 7-DoF, 10 000 samples, RQ gamma = 10;
+    published there: 848 iterations in 0.381 s = 2256 it/s on the author's workstation).  The ground truth is
+    synthetic (control points inside spheres); the perceptron trains in ONE persistent launch (dc_perceptron_train_rows)."""
+    from diffco_b200 import ForwardKinematicsDiffCo
+    from diffco_b200 import model as M
+
+    robot = M.PandaFK()
+    centres = torch.tensor([[0.45, 0.0, 0.55], [-0.1, 0.45, 0.4], [0.2, -0.4, 0.8]], dtype=torch.float32, device=dev)
+    radii = torch.tensor([0.22, 0.18, 0.2], dtype=torch.float32, device=dev)
+
+    def gt(q):
+        pts = robot.fkine(q.to(dev).float())  # (B, M, 3)
+        hit = ((pts[:, :, None, :] - centres[None, None]).norm(dim=-1) < radii).any(dim=2).any(dim=1)
+        return hit.to(q.dtype)
+
+    chk = ForwardKinematicsDiffCo(robot=robot, gt_check_func=gt, device=dev)
+    gen = torch.Generator().manual_seed(SEED)
+    lim = robot.limits.double()
+    X = (torch.rand(10000, 7, generator=gen, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]).float().to(dev)
+    labels = gt(X)
+    chk.perceptron.train(X[:512], 2 * labels[:512] - 1, max_iteration=512)  # warm-up (module load, allocator)
+    torch.cuda.synchronize(dev)
+    y = 2 * labels - 1
+    t0 = time.perf_counter()
+    chk.perceptron.train(X, y, max_iteration=len(X))
+    torch.cuda.synchronize(dev)
+    t_train = time.perf_counter() - t0
+    iters = chk.perceptron.train_iterations + 1
+    t0 = time.perf_counter()
+    rates = chk.fit(q=X, labels=labels, verify_ratio=0.1)
+    torch.cuda.synchronize(dev)
+    t_fit = time.perf_counter() - t0
+    return {"workload": "ForwardKinematicsDiffCo.fit: PandaFK (F = 21), 10000 samples (synthetic sphere obstacles, "
+                        f"{float(labels.mean()):.2f} in collision), RQKernel(10), fp32", "value": iters / t_train,
+            "unit": "training iterations/s (train_perceptron only)", "iterations": iters, "train_s": t_train,
+            "support_points": int(len(chk.perceptron.support_points)), "kernel_rows_computed": chk.perceptron.train_kernel_rows,
+            "fit_s": t_fit, "fit_note": "fit() = split + train + fit_poly(Polyharmonic(1,1)) + safety bias + verification",
+            "verify_acc_tpr_tnr": [float(v) for v in rates],
+            "published_reference": "848 it, 0.381 s loop (2256 it/s), 467 supports, author workstation CPU (BASELINE.md §1)"}
 
 
 def main():

@@ -143,6 +143,9 @@ PROTOTYPES = {
     "dc_perceptron_train": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
+    "dc_perceptron_train_rows": (C.c_int, [C.POINTER(KernelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(PeerHandle)]),
     "dc_peer_open": (C.c_int, [C.POINTER(PeerHandle), C.POINTER(C.c_void_p)]),
     "dc_peer_close": (C.c_int, [C.c_void_p]),

@@ -25,7 +25,9 @@ struct TrainArgs {
   const T* y;   // [N,C]
   T* gains;     // [N,C]
   T* hyp;       // [N,C]
-  T* kmat;      // [N,N]
+  T* kmat;      // [N,N], or compact [cap,N]: only the rows the loop asks for (slot != nullptr)
+  int* slot;    // compact storage: slot[i] = row of kmat holding K[i,:], -1 = not computed; nullptr = full N x N matrix
+  long long cap;
   T* diag;      // [N]  (== diagonal of kmat; 0 marks "row not computed yet", kernel_perceptrons.py:117)
   long long* iters_out;  // [2]: last iteration index, number of kernel rows computed
   long long n;
@@ -112,12 +114,20 @@ __global__ void __launch_bounds__(kTrainThreads, 1) perceptron_train_kernel(cons
   __shared__ long long s_ll[33];
   __shared__ T s_xi[DC_MAX_FEATURES];
   __shared__ int s_complete[DC_MAX_CLASSES];
+  __shared__ long long s_used;  // compact storage: rows handed out so far
 
   const int tid = threadIdx.x;
   const long long N = a.n;
   const int C = a.n_class, F = a.n_feat;
   const T inf = (T)INFINITY;
   if (tid < DC_MAX_CLASSES) s_complete[tid] = 0;
+  if (a.slot != nullptr) {
+    // rows pre-loaded by the caller (jump start) occupy the slots 0 .. max(slot)
+    long long mx = -1;
+    for (long long j = tid; j < N; j += kTrainThreads) mx = max(mx, (long long)a.slot[j]);
+    const ValIdx<T> top = block_argext<T, -1>((T)mx, 0, s_vi);
+    if (tid == 0) s_used = (long long)top.v + 1;
+  }
   __syncthreads();
 
   long long rows_computed = 0;
@@ -142,6 +152,19 @@ __global__ void __launch_bounds__(kTrainThreads, 1) perceptron_train_kernel(cons
       // ---- lazy kernel row: K[i] = k(X_t[i], X_t); K[:, i] = K[i] ----------------------------------------
       const bool need_row = (a.diag[i] == (T)0);
       __syncthreads();  // every thread has sampled the flag before the row's owner thread overwrites it
+      if (need_row && a.slot != nullptr) {
+        if (s_used >= a.cap) {  // out of row storage: report and stop (the caller retries with a larger capacity)
+          if (tid == 0) {
+            a.iters_out[0] = it;
+            a.iters_out[1] = -1;
+          }
+          return;
+        }
+        if (tid == 0) a.slot[i] = (int)s_used;
+        __syncthreads();
+        if (tid == 0) s_used += 1;
+      }
+      const long long ri = (a.slot != nullptr) ? (long long)a.slot[i] : i;  // row of kmat that holds K[i,:]
       if (need_row) {
         for (int f = tid; f < F; f += kTrainThreads) s_xi[f] = a.x[i * F + f];
         __syncthreads();
@@ -155,14 +178,14 @@ __global__ void __launch_bounds__(kTrainThreads, 1) perceptron_train_kernel(cons
           T k, coef;
           radial_eval<KR_GENERIC, T>(a.rc, rho, k, coef);
           k = k * a.rc.score_scale;
-          a.kmat[i * N + j] = k;
-          a.kmat[j * N + i] = k;
+          a.kmat[ri * N + j] = k;
+          if (a.slot == nullptr) a.kmat[j * N + i] = k;  // K[:, i] = K[i] (kernel_perceptrons.py:119); compact: rows only
           if (j == i) a.diag[i] = k;
         }
         ++rows_computed;
         __syncthreads();
       }
-      const T* krow = a.kmat + i * N;
+      const T* krow = a.kmat + ri * N;
 
       if (mn.v <= (T)0) {
         // delta = (beta^((1+y_i)/2) * y_i - h_i) / K_ii ; gains_i += delta ; h += delta * K[i]
@@ -198,7 +221,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) perceptron_train_kernel(cons
       if (mx.v > (T)0 && count > 1) {
         const long long r = mx.i;
         const T gr = a.gains[r * C + c];
-        const T* rrow = a.kmat + r * N;
+        const T* rrow = a.kmat + ((a.slot != nullptr) ? (long long)a.slot[r] : r) * N;  // nonzero gain => its row exists
         __syncthreads();
         for (long long j = tid; j < N; j += kTrainThreads) a.hyp[j * C + c] = add_rn(a.hyp[j * C + c], -mul_rn(gr, rrow[j]));
         if (tid == 0) a.gains[r * C + c] = (T)0;
@@ -231,8 +254,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1) perceptron_train_kernel(cons
 
 template <typename T>
 static int train_typed(const dc_kernel_desc* kernel, const void* x, const void* y, int64_t n, int32_t F, int32_t C,
-                       double beta, int64_t max_iteration, void* gains, void* hyp, void* kmat, void* diag,
-                       int32_t legacy_multi, int64_t* iters_out, cudaStream_t stream) {
+                       double beta, int64_t max_iteration, void* gains, void* hyp, void* kmat, int32_t* slot, int64_t cap,
+                       void* diag, int32_t legacy_multi, int64_t* iters_out, cudaStream_t stream) {
   TrainArgs<T> a;
   if (!make_radial_consts<T>(*kernel, &a.rc)) return DC_ERR_INVALID_ARG;
   a.x = (const T*)x;
@@ -240,6 +263,8 @@ static int train_typed(const dc_kernel_desc* kernel, const void* x, const void* 
   a.gains = (T*)gains;
   a.hyp = (T*)hyp;
   a.kmat = (T*)kmat;
+  a.slot = slot;
+  a.cap = cap;
   a.diag = (T*)diag;
   a.iters_out = (long long*)iters_out;
   a.n = n;
@@ -259,16 +284,26 @@ extern "C" int dc_perceptron_train(const dc_kernel_desc* kernel, const void* x_f
                                    int32_t n_features, int32_t n_class, int32_t dtype, double beta, int64_t max_iteration,
                                    void* gains, void* hypothesis, void* kernel_matrix, void* diag, int32_t legacy_multi,
                                    int64_t* iterations_out, dc_stream_t stream) {
+  return dc_perceptron_train_rows(kernel, x_feat, y, n, n_features, n_class, dtype, beta, max_iteration, gains, hypothesis,
+                                  kernel_matrix, nullptr, n, diag, legacy_multi, iterations_out, stream);
+}
+
+extern "C" int dc_perceptron_train_rows(const dc_kernel_desc* kernel, const void* x_feat, const void* y, int64_t n,
+                                        int32_t n_features, int32_t n_class, int32_t dtype, double beta, int64_t max_iteration,
+                                        void* gains, void* hypothesis, void* kernel_rows, int32_t* row_slot, int64_t row_capacity,
+                                        void* diag, int32_t legacy_multi, int64_t* iterations_out, dc_stream_t stream) {
+  void* kernel_matrix = kernel_rows;
   if (!kernel || !x_feat || !y || !gains || !hypothesis || !kernel_matrix || !diag || !iterations_out)
     return DC_ERR_INVALID_ARG;
+  if (row_slot != nullptr && (row_capacity < 1 || row_capacity > n)) return DC_ERR_INVALID_ARG;
   if (n < 1 || n_features < 1 || n_features > DC_MAX_FEATURES || n_class < 1 || n_class > DC_MAX_CLASSES || max_iteration < 0)
     return DC_ERR_INVALID_ARG;
   if (!legacy_multi && n_class != 1) return DC_ERR_INVALID_ARG;
   if (dtype == DC_F32)
     return dc::train_typed<float>(kernel, x_feat, y, n, n_features, n_class, beta, max_iteration, gains, hypothesis,
-                                  kernel_matrix, diag, legacy_multi, iterations_out, (cudaStream_t)stream);
+                                  kernel_matrix, row_slot, row_capacity, diag, legacy_multi, iterations_out, (cudaStream_t)stream);
   if (dtype == DC_F64)
     return dc::train_typed<double>(kernel, x_feat, y, n, n_features, n_class, beta, max_iteration, gains, hypothesis,
-                                   kernel_matrix, diag, legacy_multi, iterations_out, (cudaStream_t)stream);
+                                   kernel_matrix, row_slot, row_capacity, diag, legacy_multi, iterations_out, (cudaStream_t)stream);
   return DC_ERR_INVALID_ARG;
 }

@@ -193,23 +193,40 @@ class DiffCo(Perceptron, _FusedScorer):
         self.distance = distance.detach().to(dev).reshape(-1) if distance is not None else None
         t0 = time()
         n = len(X)
-        if update:
-            gains, Xf, K, hyp = self._jump_start(X, exist_mask.to(dev))
-        else:
-            Xf = self._features(X).contiguous()
-            gains = torch.zeros(n, dtype=dtype, device=dev)
-            hyp = torch.zeros(n, dtype=dtype, device=dev)
-            K = torch.zeros((n, n), dtype=dtype, device=dev)
-        diag = torch.diagonal(K).clone()
-        iters = torch.zeros(2, dtype=torch.int64, device=dev)
+        # Only the kernel rows the greedy loop asks for are stored (the reference zero-initialises the full N x N matrix,
+        # kernel_perceptrons.py:90-96: 400 MB at N = 10 000): rows[cap, N] + a slot map; a run that needs more rows than
+        # `cap` reports it and is repeated with cap = N (never observed with the default: supports are a small fraction).
         lib = _lib.load()
-        with torch.cuda.device(dev):
-            st = lib.dc_perceptron_train(C.byref(self.kernel_func.desc), Xf.data_ptr(), y.data_ptr(), n, Xf.shape[1], 1,
-                                         functional._dtype_code(dtype), float(self.beta), int(max_iteration),
-                                         gains.data_ptr(), hyp.data_ptr(), K.data_ptr(), diag.data_ptr(), 0,
-                                         iters.data_ptr(), functional._stream_ptr(dev))
-        _lib.check(st, "dc_perceptron_train")
-        self.train_iterations = int(iters[0].item())
+        cap = n if getattr(self, "full_kernel_rows", False) else min(n, max(2048, n // 3))
+        while True:
+            if update:
+                gains, Xf, hyp, rows0, slot = self._jump_start(X, exist_mask.to(dev))
+                cap = max(cap, len(rows0))
+                K = torch.zeros((cap, n), dtype=dtype, device=dev)
+                K[:len(rows0)] = rows0
+                diag = torch.zeros(n, dtype=dtype, device=dev)
+                e = torch.where(slot >= 0)[0]
+                diag[e] = rows0[slot[e].long(), e]
+            else:
+                Xf = self._features(X).contiguous()
+                gains = torch.zeros(n, dtype=dtype, device=dev)
+                hyp = torch.zeros(n, dtype=dtype, device=dev)
+                K = torch.zeros((cap, n), dtype=dtype, device=dev)
+                slot = torch.full((n,), -1, dtype=torch.int32, device=dev)
+                diag = torch.zeros(n, dtype=dtype, device=dev)
+            iters = torch.zeros(2, dtype=torch.int64, device=dev)
+            with torch.cuda.device(dev):
+                st = lib.dc_perceptron_train_rows(C.byref(self.kernel_func.desc), Xf.data_ptr(), y.data_ptr(), n, Xf.shape[1], 1,
+                                                  functional._dtype_code(dtype), float(self.beta), int(max_iteration),
+                                                  gains.data_ptr(), hyp.data_ptr(), K.data_ptr(), slot.data_ptr(), cap,
+                                                  diag.data_ptr(), 0, iters.data_ptr(), functional._stream_ptr(dev))
+            _lib.check(st, "dc_perceptron_train_rows")
+            it_last, rows_done = (int(v) for v in iters.tolist())
+            if rows_done >= 0 or cap == n:
+                break
+            cap = n  # out of row storage: once more with room for every row
+        self.train_iterations = it_last
+        self.train_kernel_rows = rows_done
         if verbose:
             print(f"Ended at iteration {self.train_iterations}, cost {time() - t0:.4f} secs")
             print("ACC: {}".format(torch.sum((hyp > 0) == (y > 0)) / float(len(y))))
@@ -228,7 +245,14 @@ class DiffCo(Perceptron, _FusedScorer):
         self.distance = self.distance[mask] if self.distance is not None else None
         self.gains = gains[mask]
         self.rbf_nodes = self.gains.new_zeros(len(self.gains))
-        self.kernel_matrix = K[idx[:, None], idx[None, :]]
+        # every support had its row computed, except a never-updated point kept only to have two supports (:140-141)
+        srow = slot[idx].long()
+        self.kernel_matrix = K[srow.clamp_min(0)][:, idx]
+        missing = srow < 0
+        if bool(missing.any()):
+            fill = functional.kernel_matrix(self.kernel_func.desc, Xf[idx[missing]], Xf[idx])
+            self.kernel_matrix[missing] = fill
+            self.kernel_matrix[:, missing] = fill.T
         self._valid_supports = len(self.support_points)
         self._cache.clear()
         if verbose:
@@ -245,21 +269,23 @@ class DiffCo(Perceptron, _FusedScorer):
         hyp[~exist_mask] = self.score_original(novel).reshape(-1).to(dtype)
         novel_f = self._features(novel)
         sup_f = self.support_transformed.reshape(self.valid_supports, -1).to(dtype)
-        K = torch.zeros((n, n), dtype=dtype, device=dev)
         e = torch.where(exist_mask)[0]
         v = torch.where(~exist_mask)[0]
-        K[e[:, None], e[None, :]] = self.kernel_matrix.to(dtype)
-        cross = functional.kernel_matrix(self.kernel_func.desc, sup_f, novel_f)
-        K[e[:, None], v[None, :]] = cross
-        K[v[:, None], e[None, :]] = cross.T
+        # kernel rows of the existing supports against ALL points (old block + cross block); the novel points' rows are
+        # computed by the training loop when it asks for them.  Row k belongs to the k-th existing point.
+        rows = torch.zeros((len(e), n), dtype=dtype, device=dev)
+        rows[:, e] = self.kernel_matrix.to(dtype)
+        rows[:, v] = functional.kernel_matrix(self.kernel_func.desc, sup_f, novel_f)
+        slot = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        slot[e] = torch.arange(len(e), dtype=torch.int32, device=dev)
         Xf = torch.zeros((n, sup_f.shape[1]), dtype=dtype, device=dev)
         Xf[exist_mask] = sup_f
         Xf[~exist_mask] = novel_f
         gains = torch.zeros(n, dtype=dtype, device=dev)
         gains[exist_mask] = self.gains.to(dtype)
-        check = K @ gains
+        check = rows.T @ gains[e]  # K @ gains with gains == 0 outside the existing supports
         assert torch.allclose(check, hyp, atol=1e-4), f"diff: {torch.abs(check - hyp).max()}"  # kernel_perceptrons.py:266-268
-        return gains, Xf.contiguous(), K, hyp
+        return gains, Xf.contiguous(), hyp, rows, slot
 
     @property
     def valid_supports(self):

@@ -222,6 +222,17 @@ int dc_fk_vjp(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype,
 int dc_perceptron_train(const dc_kernel_desc* kernel, const void* x_feat, const void* y, int64_t n, int32_t n_features,
                         int32_t n_class, int32_t dtype, double beta, int64_t max_iteration, void* gains, void* hypothesis,
                         void* kernel_matrix, void* diag, int32_t legacy_multi, int64_t* iterations_out, dc_stream_t stream);
+/*
+ * The same loop without the N x N kernel matrix (the reference zero-initialises one: 400 MB at N = 10 000,
+ * kernel_perceptrons.py:90-96,204-220): only the rows the loop asks for are stored, in kernel_rows[row_capacity][N];
+ * row_slot[N] (int32, IN/OUT, -1 = not computed; pre-loaded rows — the jump-start update — occupy slots 0, 1, ...) maps
+ * a training point to its row.  When row_capacity is exhausted the loop stops with iterations_out[1] = -1 and nothing
+ * else is meaningful: call again with a larger capacity (row_capacity = n can never run out).
+ */
+int dc_perceptron_train_rows(const dc_kernel_desc* kernel, const void* x_feat, const void* y, int64_t n, int32_t n_features,
+                             int32_t n_class, int32_t dtype, double beta, int64_t max_iteration, void* gains, void* hypothesis,
+                             void* kernel_rows, int32_t* row_slot, int64_t row_capacity, void* diag, int32_t legacy_multi,
+                             int64_t* iterations_out, dc_stream_t stream);
 
 /*
  * Multi-GPU (one process per GPU of one box).  dc_peer_alloc gives a zeroed device buffer plus a handle

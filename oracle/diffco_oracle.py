@@ -471,3 +471,45 @@ def weighted_step(p0, fk, score_fn, limits, wrap_fn, *, maxiter, collision_weigh
         if float(constraint.detach() if torch.is_tensor(constraint) else constraint) <= 0.5:  # optim.py:747
             break
     return p.detach(), steps
+
+
+# --------------------------------------------------------------------------------------------------
+# High-level checker (collision_checkers.py:163-218, 254-303, 475-503)
+# --------------------------------------------------------------------------------------------------
+
+
+def checker_fit(X, labels01, kernel, transform, verify_ratio, q_verify_fallback=None, init_from=None, exist_mask=None):
+    """RBFDiffCo.fit, collision_checkers.py:163-218: labels {0,1} -> +-1; with 0 < verify_ratio < 1 a random verification
+    split (torch.randperm, global RNG); train (optionally jump-started, :220-252 -> kernel_perceptrons.py:222-269) with
+    max_iteration = len(train set); fit_poly(Polyharmonic(1, 1), 'label'); safety bias = min(|min|, |max|) / 3 of poly_score
+    over the verification configurations (:497-503).  Returns (Perceptron, safety_bias, q_verify, labels_verify)."""
+    y = 2 * labels01 - 1
+    y_verify = None
+    if 0 < verify_ratio < 1:
+        n_verify = int(verify_ratio * len(X))
+        mask = torch.zeros(len(X), dtype=torch.bool)
+        mask[torch.randperm(len(X))[:n_verify]] = True
+        X_train, q_verify, y_train, y_verify = X[~mask], X[mask], y[~mask], y[mask]
+        if exist_mask is not None:
+            exist_mask = exist_mask[~mask]
+    else:
+        X_train, y_train, q_verify = X, y, q_verify_fallback
+    init = None
+    if init_from is not None:
+        init = jump_start(init_from, X_train, y_train, exist_mask, kernel, transform=transform)
+    P = train_perceptron(X_train, y_train, kernel, transform=transform, beta=1.0, max_iteration=len(X_train), init=init)
+    ph = KernelSpec("polyharmonic", 1.0, 1)
+    fit_poly(P, ph, target="label")
+    scores = poly_score(q_verify, transform, ph, P.support_transformed, P.rbf_nodes)[:, 0]
+    bias = torch.minimum(scores.min().abs(), scores.max().abs()) / 3
+    return P, bias, q_verify, y_verify
+
+
+def checker_rates(P: Perceptron, transform, q, labels_pm1, bias):
+    """RBFDiffCo.verify, collision_checkers.py:254-290: (acc, tpr, tnr) of sign(poly_score + bias) — the BIASED rates it returns."""
+    ph = KernelSpec("polyharmonic", 1.0, 1)
+    pred = 2 * (poly_score(q, transform, ph, P.support_transformed, P.rbf_nodes)[:, 0] + bias > 0).to(q.dtype) - 1
+    acc = (pred == labels_pm1).float().mean()
+    tpr = (pred[labels_pm1 == 1] == 1).float().mean()
+    tnr = (pred[labels_pm1 == -1] == -1).float().mean()
+    return acc, tpr, tnr

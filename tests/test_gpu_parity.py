@@ -389,8 +389,11 @@ def test_jump_start_update_matches_reference(dev):
     dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot.fkine, beta=1.0)
     dc.train(T64(g["p7_X"]), T64(g["p7_y"]), max_iteration=len(g["p7_X"]))
     Xu, yu, exist = T64(g["p7u_X"]), T64(g["p7u_y"]), torch.from_numpy(g["p7u_exist"])
-    gains0, _, K0, h0 = dc._jump_start(Xu.to(dev), exist.to(dev))
-    assert rel(gains0, g["p7u_gains0"]) <= 1e-9 and rel(h0, g["p7u_h0"]) <= 1e-9 and rel(K0, g["p7u_K0"]) <= 1e-12
+    gains0, _, h0, rows0, slot0 = dc._jump_start(Xu.to(dev), exist.to(dev))
+    # only the rows of the existing supports are materialised (the reference fills a full N x N matrix with them)
+    e = torch.where(exist)[0]
+    assert slot0[e.to(dev)].tolist() == list(range(len(e))) and int((slot0 >= 0).sum()) == len(e)
+    assert rel(gains0, g["p7u_gains0"]) <= 1e-9 and rel(h0, g["p7u_h0"]) <= 1e-9 and rel(rows0, g["p7u_K0"][e.numpy()]) <= 1e-12
     dc.train(Xu, yu, update=True, exist_mask=exist, max_iteration=len(Xu))
     assert dc.support_index.tolist() == g["p7u_idx"].tolist()
     assert rel(dc.gains, g["p7u_gains"]) <= 1e-8 and rel(dc.hypothesis, g["p7u_hyp"]) <= 1e-8

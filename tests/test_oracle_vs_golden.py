@@ -274,3 +274,34 @@ def test_oracle_against_live_reference():
     s, gq = O.score_and_grad(lambda z: O.score_original(z, fk, O.KernelSpec("rq", 10.0, 2), fk(S), w), q)
     close(s.numpy(), s_ref.detach().numpy(), 1e-12)
     close(gq.numpy(), qv.grad.numpy(), 1e-11)
+
+
+def test_checker_fit_update_verify_match_reference():
+    """oracle.checker_fit / checker_rates against the UNMODIFIED reference's ForwardKinematicsDiffCo (checkers.npz)."""
+    g = load("checkers.npz")
+    robot = P.make_robot("planar7")
+    fk = P.oracle_fk(robot)
+    kern = O.KernelSpec("rq", 10.0, 2)
+    X = T64(g["X"])
+    labels = (P.circle_labels(robot, X) > 0).double()
+    torch.manual_seed(5)
+    perc, bias, q_verify, y_verify = O.checker_fit(X, labels, kern, fk, verify_ratio=0.2)
+    close(perc.support_points.numpy(), g["fit_support_points"], 1e-15)
+    close(perc.rbf_nodes.numpy(), g["fit_nodes"], 1e-6)  # solve() of an ill-conditioned Polyharmonic Gram matrix: the
+    # reference lays the features out (N, 3, L), a different summation order inside cdist
+    close(q_verify.numpy(), g["fit_q_verify"], 1e-15)
+    close(np.array(float(bias)), g["fit_bias"], 1e-7)
+    rates = O.checker_rates(perc, fk, q_verify, y_verify, bias)
+    close(np.array([float(v) for v in rates]), g["fit_rates"], 1e-6)
+    Q = T64(g["Q"])
+    ph = O.KernelSpec("polyharmonic", 1.0, 1)
+    close((O.poly_score(Q, fk, ph, perc.support_transformed, perc.rbf_nodes) + bias).numpy(), g["fit_collision_score"].reshape(64, 1), 1e-7)
+    Xu, exist = T64(g["upd_X"]), torch.from_numpy(g["upd_exist"])
+    lab_u = (P.circle_labels(robot, Xu) > 0).double()
+    perc2, bias2, _, _ = O.checker_fit(Xu, lab_u, kern, fk, verify_ratio=0, q_verify_fallback=T64(g["upd_q_verify"]),
+                                       init_from=perc, exist_mask=exist)
+    close(perc2.support_points.numpy(), g["upd_support_points"], 1e-15)
+    close(np.array(float(bias2)), g["upd_bias"], 1e-7)
+    close((O.poly_score(Q, fk, ph, perc2.support_transformed, perc2.rbf_nodes) + bias2).numpy(), g["upd_collision_score"], 1e-7)
+    lab_q = 2 * (P.circle_labels(robot, Q) > 0).double() - 1
+    close(np.array([float(v) for v in O.checker_rates(perc2, fk, Q, lab_q, bias2)]), g["upd_verify_rates"], 1e-6)
