@@ -20,10 +20,10 @@ DC_MAX_TOOL_POINTS = 2
 DC_MAX_FEATURES = 64
 DC_MAX_CLASSES = 8
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 DC_F32, DC_F64 = 0, 1
 DC_FK_NONE, DC_FK_PLANAR_CHAIN, DC_FK_SE2_BODY, DC_FK_SE3_BODY, DC_FK_DH_ARMS, DC_FK_SE2_BASE_PLANAR_ARM = range(6)
-DC_K_RQ, DC_K_POLYHARMONIC, DC_K_MULTIQUADRIC = 1, 2, 3
+DC_K_RQ, DC_K_POLYHARMONIC, DC_K_MULTIQUADRIC, DC_K_RQ_TEMPORAL = 1, 2, 3, 4
 DC_GRAD_NONE, DC_GRAD_SUM, DC_GRAD_JAC = 0, 1, 2
 
 
@@ -54,6 +54,8 @@ class FkDesc(C.Structure):
         ("n_arms", C.c_int32),
         ("n_keypoints", C.c_int32),
         ("n_links", C.c_int32),
+        ("n_repeat", C.c_int32),
+        ("time_last", C.c_int32),
         ("reserved", C.c_int32),
         ("link_length", C.c_double * DC_MAX_LINKS),
         ("keypoints", (C.c_double * DC_MAX_KEYPOINTS) * 3),
@@ -66,7 +68,8 @@ class FkDesc(C.Structure):
 
 
 class KernelDesc(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("order", C.c_int32), ("param", C.c_double)]
+    _fields_ = [("kind", C.c_int32), ("order", C.c_int32), ("param", C.c_double), ("param2", C.c_double),
+                ("alpha", C.c_double), ("order2", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Supports(C.Structure):

@@ -74,31 +74,37 @@ static bool fk_valid(const dc_fk_desc& fk) {
   if (fk.dof < 1) return false;
   const int F = fk_n_features(fk);
   if (F < 1 || F > DC_MAX_FEATURES) return false;
+  // composite maps: the per-type rules below apply to ONE block of din columns / fin features
+  const int rep = fk.n_repeat > 1 ? fk.n_repeat : 1, tl = fk.time_last ? 1 : 0;
+  const bool composite = rep > 1 || tl;
+  if (fk.type == DC_FK_NONE) return !composite;
+  if (fk.dof > DC_MAX_DOF || (fk.dof - tl) % rep || (F - tl) % rep) return false;
+  const int din = (fk.dof - tl) / rep, fin = (F - tl) / rep;
+  if (din < 1 || fin < 1) return false;
+  if (composite ? fk.point_dim != 1 : fk.point_dim < 1) return false;
+  const auto points = [&](int dim, int m) { return fin == dim * m && (composite || (fk.point_dim == dim && fk.n_points == m)); };
   switch (fk.type) {
-    case DC_FK_NONE:
-      return true;
     case DC_FK_PLANAR_CHAIN:
-      return fk.dof <= DC_MAX_DOF && fk.n_links == fk.dof && fk.n_links <= DC_MAX_LINKS && fk.point_dim == 2 &&
-             fk.n_points == fk.dof;
+      return fk.n_links == din && fk.n_links <= DC_MAX_LINKS && points(2, din);
     case DC_FK_SE2_BODY:
-      return fk.dof == 3 && fk.point_dim == 2 && fk.n_keypoints == fk.n_points && fk.n_keypoints <= DC_MAX_KEYPOINTS;
+      return din == 3 && fk.n_keypoints <= DC_MAX_KEYPOINTS && points(2, fk.n_keypoints);
     case DC_FK_SE3_BODY:
-      return fk.dof == 6 && fk.point_dim == 3 && fk.n_keypoints == fk.n_points && fk.n_keypoints <= DC_MAX_KEYPOINTS;
+      return din == 6 && fk.n_keypoints <= DC_MAX_KEYPOINTS && points(3, fk.n_keypoints);
     case DC_FK_SE2_BASE_PLANAR_ARM:
-      return fk.dof == 3 + fk.n_links && fk.dof <= DC_MAX_DOF && fk.point_dim == 2 &&
-             fk.n_points == fk.n_keypoints + fk.n_links && fk.n_keypoints <= DC_MAX_KEYPOINTS;
+      return din == 3 + fk.n_links && fk.n_keypoints <= DC_MAX_KEYPOINTS && points(2, fk.n_keypoints + fk.n_links);
     case DC_FK_DH_ARMS: {
-      if (fk.dof > DC_MAX_DOF || fk.point_dim != 3 || fk.n_arms < 1 || fk.n_arms > DC_MAX_ARMS) return false;
+      if (fin % 3 || !points(3, fin / 3) || fk.n_arms < 1 || fk.n_arms > DC_MAX_ARMS) return false;
+      const int m = fin / 3;
       for (int a = 0; a < fk.n_arms; ++a) {
         const dc_dh_arm& arm = fk.arms[a];
         if (arm.n_joints < 1 || arm.n_joints > DC_MAX_ARM_JOINTS || arm.n_tool < 0 || arm.n_tool > DC_MAX_TOOL_POINTS)
           return false;
         for (int i = 0; i < arm.n_joints; ++i) {
-          if (arm.joint_index[i] < 0 || arm.joint_index[i] >= fk.dof) return false;
-          if (arm.out_slot[i] >= fk.n_points) return false;
+          if (arm.joint_index[i] < 0 || arm.joint_index[i] >= din) return false;
+          if (arm.out_slot[i] >= m) return false;
         }
         for (int k = 0; k < arm.n_tool; ++k)
-          if (arm.tool_slot[k] < 0 || arm.tool_slot[k] >= fk.n_points) return false;
+          if (arm.tool_slot[k] < 0 || arm.tool_slot[k] >= m) return false;
       }
       return true;
     }
@@ -137,13 +143,18 @@ __global__ void __launch_bounds__(128) kernel_matrix_kernel(RadialConsts<T> rc, 
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nb) return;
   const T* xj = xb + j * F;
+  const bool temporal = rc.kind == DC_K_RQ_TEMPORAL;
+  const int Fx = temporal ? F - 1 : F;
   T rho = (T)0;
-  for (int f = 0; f < F; ++f) {
+  for (int f = 0; f < Fx; ++f) {
     const T d = xi[f] - xj[f];
     rho = fma(d, d, rho);
   }
-  T k, coef;
-  radial_eval<KR_GENERIC, T>(rc, rho, k, coef);
+  T k, coef, coef_t;
+  if (temporal)
+    radial_eval_temporal<T>(rc, rho, xi[F - 1] - xj[F - 1], k, coef, coef_t);
+  else
+    radial_eval<KR_GENERIC, T>(rc, rho, k, coef);
   out[i * nb + j] = k * rc.score_scale;
 }
 

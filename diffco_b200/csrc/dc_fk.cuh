@@ -245,7 +245,7 @@ __device__ void fk_dh_arm_vjp(const dc_dh_arm& arm, const T* q, Strided<T> x, St
 
 // ---- dispatch ----------------------------------------------------------------------------------------
 template <typename T>
-__device__ __noinline__ void fk_forward(const dc_fk_desc& fk, const T* q, T* xp, int ld) {
+__device__ __forceinline__ void fk_forward_one(const dc_fk_desc& fk, const T* q, T* xp, int ld) {
   Strided<T> x{xp, ld};
   switch (fk.type) {
     case DC_FK_NONE:
@@ -273,6 +273,22 @@ __device__ __noinline__ void fk_forward(const dc_fk_desc& fk, const T* q, T* xp,
     default:
       break;
   }
+}
+
+// Composite maps (dc_fk_desc.n_repeat / time_last): the map above applied to n_repeat consecutive blocks of q with the
+// features concatenated (LineFKKernel, kernel.py:145-173) and / or a trailing time column passed through as the last
+// feature (TemporalFKKernel, kernel.py:175-202).
+__device__ __forceinline__ int fk_total_features(const dc_fk_desc& fk) {
+  return fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim;
+}
+__device__ __forceinline__ bool fk_composite(const dc_fk_desc& fk) { return fk.n_repeat > 1 || fk.time_last != 0; }
+
+template <typename T>
+__device__ __noinline__ void fk_forward(const dc_fk_desc& fk, const T* q, T* xp, int ld) {
+  const int rep = fk.n_repeat > 1 ? fk.n_repeat : 1, tl = fk.time_last ? 1 : 0;
+  const int din = (fk.dof - tl) / rep, fin = (fk_total_features(fk) - tl) / rep;
+  for (int r = 0; r < rep; ++r) fk_forward_one<T>(fk, q + r * din, xp + (size_t)r * fin * ld, ld);
+  if (tl) xp[(size_t)rep * fin * ld] = q[fk.dof - 1];
 }
 
 // sin / cos in float64 to ~1e-13 absolute — all the (hi, lo) float32 feature pairs need (lo is ~1e-7 of hi) — at a
@@ -337,7 +353,7 @@ __device__ __forceinline__ void fk_planar_f64_reg(const double* link, int n, con
 template <bool WITH_LO>
 __device__ __noinline__ void fk_forward_f32x(const dc_fk_desc& fk, const float* q, float* xh, int ldh, float* xl, int ldl) {
   double qd[DC_MAX_DOF], xd[DC_MAX_FEATURES];
-  if (fk.type == DC_FK_PLANAR_CHAIN && fk.n_links <= 8) {
+  if (fk.type == DC_FK_PLANAR_CHAIN && fk.n_links <= 8 && !fk_composite(fk)) {
     fk_planar_f64_reg<8>(fk.link_length, fk.n_links, q, xd);
   } else {
 #pragma unroll
@@ -364,7 +380,7 @@ __device__ __forceinline__ void fk_features(const dc_fk_desc& fk, const double* 
 }
 
 template <typename T>
-__device__ __noinline__ void fk_vjp(const dc_fk_desc& fk, const T* q, T* xp, int ldx, T* gp, int ldg, T* gq) {
+__device__ __forceinline__ void fk_vjp_one(const dc_fk_desc& fk, const T* q, T* xp, int ldx, T* gp, int ldg, T* gq) {
   Strided<T> x{xp, ldx};
   Strided<T> g{gp, ldg};
   switch (fk.type) {
@@ -401,6 +417,15 @@ __device__ __noinline__ void fk_vjp(const dc_fk_desc& fk, const T* q, T* xp, int
     default:
       break;
   }
+}
+
+template <typename T>
+__device__ __noinline__ void fk_vjp(const dc_fk_desc& fk, const T* q, T* xp, int ldx, T* gp, int ldg, T* gq) {
+  const int rep = fk.n_repeat > 1 ? fk.n_repeat : 1, tl = fk.time_last ? 1 : 0;
+  const int din = (fk.dof - tl) / rep, fin = (fk_total_features(fk) - tl) / rep;
+  for (int r = 0; r < rep; ++r)
+    fk_vjp_one<T>(fk, q + r * din, xp + (size_t)r * fin * ldx, ldx, gp + (size_t)r * fin * ldg, ldg, gq + r * din);
+  if (tl) gq[fk.dof - 1] = gp[(size_t)rep * fin * ldg];
 }
 
 }  // namespace dc

@@ -8,6 +8,10 @@
 //   Polyharmonic(k odd)    k = r^k           coef = k r^(k-2)        scales 1/eps
 //   Polyharmonic(k even)   k = r^k log r (0 at 0)   coef = r^(k-2) (k log r + 1) (0 at 0)            scales 1/eps
 //   MultiQuadratic(eps)    kernel.py:45-57   k = sqrt(rho/eps^2+1)  coef = 1/k     grad_scale = 1/eps^2
+//   TemporalFKKernel       kernel.py:175-202 the last feature is time: rho_x over the first F-1 features, dt the last
+//                          difference; ux = 1/(1+gx/px rho_x), ut = 1/(1+gt/pt dt^2), k = ux^px (ut^pt)^alpha,
+//                          coef = ux k for the space features, coef_t = (gt/gx) alpha ut k for the time feature
+//                          (radial_eval_temporal); grad_scale = -2 gx
 //
 // The r = 0 sub-gradient of Polyharmonic(1) is 0, matching torch.cdist's backward: rho is
 // clamped to a tiny positive value before MUFU.RSQ, so coef stays finite and multiplies an exactly-zero
@@ -27,12 +31,17 @@ struct RadialConsts {
   T grad_scale;   // applied to sum w coef (x - s)
   int kind;       // dc_kernel_kind (generic path)
   int order;      // p or k       (generic path)
+  // DC_K_RQ_TEMPORAL only
+  T c0_t;         // gamma_t / p_t
+  T alpha_pt;     // alpha * p_t: (ut^pt)^alpha = ut^(alpha pt)
+  T coef_t_scale; // (gamma_t / gamma_x) * alpha
 };
 
 template <typename T>
 __host__ inline bool make_radial_consts(const dc_kernel_desc& k, RadialConsts<T>* out) {
   out->kind = k.kind;
   out->order = k.order;
+  out->c0_t = out->alpha_pt = out->coef_t_scale = (T)0;
   switch (k.kind) {
     case DC_K_RQ:
       if (k.order < 1) return false;
@@ -52,6 +61,15 @@ __host__ inline bool make_radial_consts(const dc_kernel_desc& k, RadialConsts<T>
       out->score_scale = (T)1;
       out->grad_scale = (T)(1.0 / (k.param * k.param));
       return true;
+    case DC_K_RQ_TEMPORAL:
+      if (k.order < 1 || k.order2 < 1 || k.param == 0.0) return false;
+      out->c0 = (T)(k.param / k.order);
+      out->score_scale = (T)1;
+      out->grad_scale = (T)(-2.0 * k.param);
+      out->c0_t = (T)(k.param2 / k.order2);
+      out->alpha_pt = (T)(k.alpha * k.order2);
+      out->coef_t_scale = (T)(k.param2 / k.param * k.alpha);
+      return true;
     default:
       return false;
   }
@@ -66,6 +84,8 @@ inline int fast_radial_kind(const dc_kernel_desc& k) {
 
 __device__ __forceinline__ float log_t(float x) { return logf(x); }
 __device__ __forceinline__ double log_t(double x) { return log(x); }
+__device__ __forceinline__ float pow_t(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ double pow_t(double x, double y) { return pow(x, y); }
 
 template <typename T>
 __device__ __forceinline__ T ipow(T b, int e) {
@@ -119,6 +139,17 @@ __device__ __forceinline__ void radial_eval(const RadialConsts<T>& rc, T rho, T&
       }
     }
   }
+}
+
+// DC_K_RQ_TEMPORAL: rho_x = |dx|^2 over the space features, dt = the time difference.  coef multiplies the space
+// differences and coef_t the time difference, both under the common grad_scale = -2 gamma_x.
+template <typename T>
+__device__ __forceinline__ void radial_eval_temporal(const RadialConsts<T>& rc, T rho_x, T dt, T& k, T& coef, T& coef_t) {
+  const T ux = fast_rcp(fma(rho_x, rc.c0, (T)1));
+  const T ut = fast_rcp(fma(dt * dt, rc.c0_t, (T)1));
+  k = ipow(ux, rc.order) * pow_t(ut, rc.alpha_pt);
+  coef = ux * k;
+  coef_t = rc.coef_t_scale * ut * k;
 }
 
 // Packed form for the thread-per-query kernel: both halves of the pair are different QUERIES against the same support

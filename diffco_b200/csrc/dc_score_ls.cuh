@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(kLsWarps * 32) score_ls_kernel(const __grid_co
     for (int c = 0; c < DC_MAX_CLASSES; ++c) sc[c] = (T)0;
 #pragma unroll
     for (int e = 0; e < (GRAD ? RW : 1); ++e) g[e] = (T)0;
+    T gt = (T)0;
+    const bool temporal = a.rc.kind == DC_K_RQ_TEMPORAL;
+    const int Fx = temporal ? F - 1 : F;  // features that enter rho
 
     // Small rows: keep the query features and the difference vector in registers.  Large rows (F > 32 fp32 /
     // F > 16 fp64): re-read x from shared memory and the row from L1 for the gradient update instead.
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(kLsWarps * 32) score_ls_kernel(const __grid_co
 #pragma unroll
         for (int e = 0; e < RW; ++e) {
           d[e] = (e < F) ? xr[e] + row[e] : (T)0;  // table holds -s; entries past F are weights / padding
-          rho = fma(d[e], d[e], rho);
+          rho = fma(d[e], (e < Fx) ? d[e] : (T)0, rho);
         }
       } else {
 #pragma unroll
@@ -157,13 +160,18 @@ __global__ void __launch_bounds__(kLsWarps * 32) score_ls_kernel(const __grid_co
           load4<T>(rp + 4 * j, d);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const T dv = (4 * j + e < F) ? xq[4 * j + e] + d[e] : (T)0;
+            const T dv = (4 * j + e < Fx) ? xq[4 * j + e] + d[e] : (T)0;
             rho = fma(dv, dv, rho);
           }
         }
       }
-      T k, coef;
-      radial_eval<KR_GENERIC, T>(a.rc, rho, k, coef);
+      T k, coef, coef_t = (T)0, dt = (T)0;
+      if (temporal) {  // the last feature is time (kernel.py:175-202): it leaves rho and gets its own coefficient
+        dt = xq[F - 1] + __ldg(rp + F - 1);
+        radial_eval_temporal<T>(a.rc, rho, dt, k, coef, coef_t);
+      } else {
+        radial_eval<KR_GENERIC, T>(a.rc, rho, k, coef);
+      }
       T om = (T)0;
 #pragma unroll
       for (int c = 0; c < DC_MAX_CLASSES; ++c) {
@@ -175,6 +183,7 @@ __global__ void __launch_bounds__(kLsWarps * 32) score_ls_kernel(const __grid_co
       }
       if (GRAD) {
         const T cv = om * coef;
+        gt = fma(om * (coef_t - coef), dt, gt);  // corrects the last feature's term below; 0 unless temporal
         if constexpr (KEEP) {
 #pragma unroll
           for (int e = 0; e < RW; ++e) g[e] = fma(cv, d[e], g[e]);
@@ -207,6 +216,10 @@ __global__ void __launch_bounds__(kLsWarps * 32) score_ls_kernel(const __grid_co
           const T v = warp_sum(g[e]);
           if (lane == 0) part[warp][DC_MAX_CLASSES + e] = v;
         }
+      }
+      if (temporal) {
+        const T v = warp_sum(gt);
+        if (lane == 0) part[warp][DC_MAX_CLASSES + F - 1] += v;
       }
     }
     __syncthreads();

@@ -42,8 +42,6 @@ __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, 
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float pow_t(float a, float b) { return powf(a, b); }
-__device__ __forceinline__ double pow_t(double a, double b) { return pow(a, b); }
 
 template <typename T>
 struct ValIdx {
@@ -170,13 +168,18 @@ __global__ void __launch_bounds__(kTrainThreads, 1) perceptron_train_kernel(cons
         __syncthreads();
         for (long long j = tid; j < N; j += kTrainThreads) {
           const T* xj = a.x + j * F;
+          const bool temporal = a.rc.kind == DC_K_RQ_TEMPORAL;
+          const int Fx = temporal ? F - 1 : F;
           T rho = (T)0;
-          for (int f = 0; f < F; ++f) {
+          for (int f = 0; f < Fx; ++f) {
             const T d = s_xi[f] - xj[f];
             rho = fma(d, d, rho);
           }
-          T k, coef;
-          radial_eval<KR_GENERIC, T>(a.rc, rho, k, coef);
+          T k, coef, coef_t;
+          if (temporal)
+            radial_eval_temporal<T>(a.rc, rho, s_xi[F - 1] - xj[F - 1], k, coef, coef_t);
+          else
+            radial_eval<KR_GENERIC, T>(a.rc, rho, k, coef);
           k = k * a.rc.score_scale;
           a.kmat[ri * N + j] = k;
           if (a.slot == nullptr) a.kmat[j * N + i] = k;  // K[:, i] = K[i] (kernel_perceptrons.py:119); compact: rows only

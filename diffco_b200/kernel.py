@@ -102,3 +102,89 @@ class FKKernel(KernelFunc):
         if x_primes_controls is None:
             x_primes_controls = self.fkine(x_primes).reshape(len(x_primes), -1)
         return self.rq_kernel(xs_controls, x_primes_controls)
+
+
+def _robot_of(fkine):
+    owner = getattr(fkine, "__self__", None)
+    if owner is None or getattr(owner, "fk_desc", None) is None:
+        raise TypeError("fkine must be the bound .fkine of a diffco_b200.model robot")
+    return owner
+
+
+class _TemporalRQ(KernelFunc):
+    """The radial part of TemporalFKKernel on features [x | t]: RQ(gamma, p)(|dx|^2) * RQ(gamma_t, p_t)(dt^2)^alpha
+    (DC_K_RQ_TEMPORAL, evaluated per pair in registers like every other kernel)."""
+
+    squeeze_single_row = True  # both factors are RQKernel results (kernel.py:26-27)
+
+    def __init__(self, rq, t_rq, alpha):
+        if not isinstance(rq, RQKernel) or not isinstance(t_rq, RQKernel):
+            raise TypeError("TemporalFKKernel: both kernels must be RQKernel")
+        self.desc = KernelDesc(_lib.DC_K_RQ_TEMPORAL, rq.p, float(rq.gamma), float(t_rq.gamma), float(alpha), t_rq.p, 0)
+
+    def __call__(self, xs, x_primes):
+        return self._matrix(xs, x_primes)
+
+
+class TemporalFKKernel(KernelFunc):
+    """kernel.py:175-202 — k((q1,t1),(q2,t2)) = rq(FK(q1), FK(q2)) * t_rq(t1, t2)^alpha; time is the last column.
+    ``DiffCo`` unpacks it into (``map``: [q | t] -> [FK(q) | t], ``radial``) and fuses both into the score kernel."""
+
+    def __init__(self, fkine, rqkernel, t_rqkernel, alpha=0.5):
+        from .model import ComposedMap
+
+        self.fkine = fkine
+        self.rqkernel = rqkernel
+        self.t_rqkernel = t_rqkernel
+        self.alpha = alpha
+        self.map = ComposedMap(_robot_of(fkine), 1, time_last=True)
+        self.radial = _TemporalRQ(rqkernel, t_rqkernel, alpha)
+        self.desc = self.radial.desc
+
+    def __call__(self, xs, x_primes):
+        if xs.ndim == 1:
+            xs = xs[None, :]
+        return self.radial(self.map.fkine(xs).reshape(len(xs), -1), self.map.fkine(x_primes).reshape(len(x_primes), -1))
+
+
+class LineFKKernel(KernelFunc):
+    """kernel.py:188-202 — rq on the concatenated features of a segment's two end configurations ([q_a | q_b] rows).
+    ``DiffCo`` unpacks it into (``map``: FK on both halves, ``radial`` = the RQ kernel)."""
+
+    def __init__(self, fkine, rq_kernel):
+        from .model import ComposedMap
+
+        self.fkine = fkine
+        self.rq_kernel = rq_kernel
+        self.map = ComposedMap(_robot_of(fkine), 2)
+        self.radial = rq_kernel
+        self.desc = rq_kernel.desc
+
+    def __call__(self, xs, x_primes):
+        if xs.ndim == 1:
+            xs = xs[None, :]
+        if x_primes.ndim == 1:
+            x_primes = x_primes[None, :]
+        if xs.shape[1] != x_primes.shape[1] or xs.shape[1] % 2:
+            raise AssertionError("LineFKKernel: rows are [q_a | q_b]")
+        return self.rq_kernel(self.map.fkine(xs).reshape(len(xs), -1), self.map.fkine(x_primes).reshape(len(x_primes), -1))
+
+
+class LineKernel(KernelFunc):
+    """kernel.py:175-186 — mean of a point kernel on the two halves of [q_a | q_b] rows.  A sum of two radial kernels
+    is not radial, so it has no fused descriptor: usable as a kernel matrix (two dc_kernel_matrix launches), not as
+    ``DiffCo``'s score kernel."""
+
+    def __init__(self, point_kernel):
+        self.point_kernel = point_kernel
+
+    def __call__(self, xs, x_primes):
+        if xs.ndim == 1:
+            xs = xs[None, :]
+        if x_primes.ndim == 1:
+            x_primes = x_primes[None, :]
+        if xs.shape[1] != x_primes.shape[1] or xs.shape[1] % 2:
+            raise AssertionError("LineKernel: rows are [q_a | q_b]")
+        dof = xs.shape[1] // 2
+        pk = self.point_kernel
+        return (pk._matrix(xs[:, :dof], x_primes[:, :dof]) + pk._matrix(xs[:, dof:], x_primes[:, dof:])) / 2

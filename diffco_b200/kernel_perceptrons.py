@@ -66,7 +66,7 @@ class _SupportCache:
 
     def get(self, name, feats, weights, kfun=None, lo_fn=None):
         kdesc = getattr(kfun, "desc", None)
-        kkey = None if kdesc is None else (kdesc.kind, kdesc.order, kdesc.param)
+        kkey = None if kdesc is None else (kdesc.kind, kdesc.order, kdesc.param, kdesc.param2, kdesc.alpha, kdesc.order2)
         key = (self._key(feats), self._key(weights), kkey)
         hit = self._entries.get(name)
         if hit is None or hit[0] != key:
@@ -145,6 +145,11 @@ class DiffCo(Perceptron, _FusedScorer):
         if isinstance(self.kernel_func, kernel.FKKernel):
             transform = self.kernel_func.fkine
             self.kernel_func = self.kernel_func.rq_kernel
+        elif isinstance(self.kernel_func, (kernel.LineFKKernel, kernel.TemporalFKKernel)):
+            # kernel.py:145-202: rows are [q_a | q_b] segments / [q | t] space-time points; the composite feature map and
+            # the radial part are fused into the score kernel like a plain robot + RQ kernel
+            transform = self.kernel_func.map.fkine
+            self.kernel_func = self.kernel_func.radial
         if not isinstance(self.kernel_func, kernel.KernelFunc) or self.kernel_func.desc is None:
             raise TypeError("kernel_func must be 'rq' or a diffco_b200.kernel radial kernel")
         self.beta = beta

@@ -86,6 +86,38 @@ class Model:
         return wrap2pi(q)
 
 
+class ComposedMap(Model):
+    """A robot's feature map applied to ``n_repeat`` consecutive blocks of the input and / or with a trailing time
+    column passed through: the maps inside the reference's LineFKKernel (kernel.py:145-173; a path segment's two end
+    configurations side by side, features concatenated) and TemporalFKKernel (kernel.py:175-202; [q | t] -> [FK(q) | t]).
+    Compiles to the robot's own ``dc_fk_desc`` with ``n_repeat`` / ``time_last`` set, so the composite is fused into
+    the score kernel like any robot.  ``fkine`` returns (B, F_total, 1)."""
+
+    def __init__(self, robot, n_repeat: int = 1, time_last: bool = False):
+        base = robot.fk_desc
+        if base is None or base.type == _lib.DC_FK_NONE or base.n_repeat > 1 or base.time_last:
+            raise TypeError("ComposedMap wraps a diffco_b200.model robot")
+        if n_repeat < 1:
+            raise ValueError("n_repeat must be >= 1")
+        tl = 1 if time_last else 0
+        d = FkDesc.from_buffer_copy(base)
+        d.dof = base.dof * n_repeat + tl
+        d.n_points = base.n_features * n_repeat + tl
+        d.point_dim = 1
+        d.n_repeat = n_repeat
+        d.time_last = tl
+        if d.dof > _lib.DC_MAX_DOF or d.n_points > _lib.DC_MAX_FEATURES:
+            raise ValueError(f"composite map too large: {d.dof} columns / {d.n_points} features "
+                             f"(limits {_lib.DC_MAX_DOF} / {_lib.DC_MAX_FEATURES})")
+        self.robot = robot
+        self.fk_desc = d
+        self.dof = d.dof
+        lim = torch.as_tensor(robot.limits)
+        parts = [lim] * n_repeat + ([torch.tensor([[0.0, 1.0]], dtype=lim.dtype)] if tl else [])
+        self.limits = torch.cat(parts, dim=0)
+        self._finalize()
+
+
 class RevolutePlanarRobot(Model):
     """model.py:23-76 — planar revolute chain; fkine = cumulative link end points (model.py:40-48)."""
 

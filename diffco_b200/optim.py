@@ -12,8 +12,11 @@ diffco_b200/trajopt.py): the penalty (collision hinge + max-move + joint-limit +
 the Adam update and ``robot.wrap`` are ONE launch (``dc_traj_step``) after ``dc_score_grad``, both captured in a CUDA graph
 that is replayed per iteration.
 
-Not provided: ``trustconstr_traj_optimize`` (needs second derivatives of dist_est; optim.py:380-391) and
-``gradient_free_traj_optimize`` — both raise NotImplementedError rather than silently doing something else.
+``trustconstr_traj_optimize`` needs the Hessian of the collision constraint (optim.py:380-391); the fused score gives
+first derivatives analytically, so the Hessian is a central difference of that analytic gradient with ALL perturbed
+paths evaluated in one ``dist_est`` launch (``_SlsqpProblem.hess_con_collision``).
+
+Not provided: ``gradient_free_traj_optimize`` — raises NotImplementedError rather than silently doing something else.
 """
 from __future__ import annotations
 
@@ -22,7 +25,7 @@ from collections import namedtuple
 
 import numpy as np
 import torch
-from scipy.optimize import minimize
+from scipy.optimize import NonlinearConstraint, minimize
 
 from . import utils
 
@@ -222,6 +225,46 @@ class _SlsqpProblem:
                                                  strategy="reverse-mode")
         return jac[:, 1:-1].numpy().reshape(jac.shape[0], -1)
 
+    def hess_con_collision(self, x, v, fd_step=1e-3):
+        """sum_k v_k Hessian(c_k)(x) for trust-constr (optim.py:380-391, where it is a double-backward through the
+        reference's autograd kernel).  Here: central differences of the analytic gradient of v . c — the 2n perturbed
+        paths are densified with the base path's point counts (the structure autograd would hold fixed too), scored in
+        ONE dist_est launch and back-propagated in one backward.  fd_step 1e-3 suits a float32 model (gradient noise
+        ~1e-6 of its maximum); a float64 model tolerates 1e-5.  Counts every evaluated point in cnt_check."""
+        base = self.full_path(x).detach()
+        dof = base.shape[1]
+        n = base[1:-1].numel()
+        v = torch.as_tensor(np.asarray(v), dtype=base.dtype)
+        steps, max_step = utils.segment_steps(base, self.max_speed, None)
+        seg_index = torch.repeat_interleave(torch.arange(len(base) - 1), steps)
+        first = torch.cumsum(steps, 0) - steps
+        k = (torch.arange(len(seg_index)) - first[seg_index]).to(base.dtype).reshape(1, -1, 1)
+        paths = base.repeat(2 * n, 1, 1)
+        bump = fd_step * torch.eye(n, dtype=base.dtype).reshape(n, -1, dof)
+        paths[:n, 1:-1] += bump
+        paths[n:, 1:-1] -= bump
+        paths.requires_grad_(True)
+        delta = paths[:, 1:] - paths[:, :-1]
+        dist = delta.norm(dim=-1, keepdim=True)
+        unit = delta * max_step / torch.where(dist > 0, dist, torch.ones_like(dist))
+        pts = paths[:, :-1][:, seg_index] + k * unit[:, seg_index]  # (2n, M-1, dof): dense paths without the last waypoint
+        inner = pts[:, 1:]                                          # the reference scores dense[1:-1]
+        n_pt, n_seg = inner.shape[1], len(base) - 1
+        slack = -(self.dist_est(inner.reshape(-1, dof)).reshape(2 * n, n_pt) - self.safety_margin)
+        self.cnt_check += 2 * n * (n_pt + 2)
+        slack = torch.clamp(slack, max=0)
+        width = -(-n_pt // n_seg)
+        if n_seg * width != n_pt:
+            slack = torch.cat([slack, torch.zeros(2 * n, n_seg * width - n_pt, dtype=slack.dtype)], dim=1)
+        con = slack.reshape(2 * n, n_seg, width).sum(dim=2)
+        total = (con * v.to(con.dtype)).sum()
+        if not total.requires_grad:
+            return np.zeros((n, n))
+        (grad,) = torch.autograd.grad(total, paths)
+        g = grad[:, 1:-1].reshape(2 * n, n).double()
+        hess = (g[:n] - g[n:]) / (2 * fd_step)
+        return (0.5 * (hess + hess.T)).numpy()
+
     # joint limits (optim.py:220-236) ----------------------------------------------------------------------------
     def con_joint_limit(self, x):
         p = self.full_path(x)
@@ -275,8 +318,39 @@ def givengrad_traj_optimize(robot, dist_est, start_cfg, target_cfg, options):
 
 
 def trustconstr_traj_optimize(robot, dist_est, start_cfg, target_cfg, options):
-    raise NotImplementedError("trust-constr needs Hessian-vector products of dist_est (optim.py:380-391); the fused CUDA "
-                              "score provides first derivatives only — use givengrad_traj_optimize or adam_traj_optimize")
+    """optim.py:324-507.  scipy trust-constr on the path length with the collision constraint (Jacobian + Hessian) and the
+    joint limits; random restarts until scipy reports success, otherwise the least-violating result.  The record carries
+    scipy's result under ``info`` like the reference's.  ``options['hess_fd_step']`` (default 1e-3) is the step of the
+    finite-difference Hessian."""
+    n_waypoints, n_trials, maxiter = options["N_WAYPOINTS"], options["NUM_RE_TRIALS"], options["MAXITER"]
+    safety_margin, max_speed = options["safety_margin"], options["max_speed"]
+    fd_step = options.get("hess_fd_step", 1e-3)
+    seed = options["seed"]
+    torch.manual_seed(seed)
+    t0 = time.time()
+    cnt_check, success, best, best_violation, best_problem = 0, False, None, np.inf, None
+    for trial in range(n_trials):
+        path, trivial = _initial_path(robot, start_cfg, target_cfg, n_waypoints, trial, options)
+        if trivial:
+            return _trivial_record(robot, path, start_cfg, target_cfg, seed, t0)
+        prob = _SlsqpProblem(robot, dist_est, path, safety_margin, max_speed)
+        res = minimize(prob.cost, path[1:-1].reshape(-1).numpy(), jac=prob.grad_cost, method="trust-constr",
+                       constraints=[NonlinearConstraint(prob.con_collision, 0, np.inf, jac=prob.jac_con_collision,
+                                                        hess=lambda x, v: prob.hess_con_collision(x, v, fd_step)),
+                                    NonlinearConstraint(prob.con_joint_limit, 0, np.inf, jac=prob.grad_con_joint_limit)],
+                       options={"maxiter": maxiter, **options.get("extra_optimizer_options", {})})
+        if res.success:
+            success, best, best_problem = True, res, prob
+            cnt_check += prob.cnt_check
+            break
+        violation = -(prob.con_collision(res.x).sum() + prob.con_joint_limit(res.x))
+        cnt_check += prob.cnt_check
+        if violation < best_violation:
+            best_violation, best, best_problem = violation, res, prob
+    solution = best_problem.full_path(best.x).detach()
+    return {"start_cfg": _cfg_list(start_cfg), "target_cfg": _cfg_list(target_cfg), "cnt_check": cnt_check,
+            "cost": float(best.fun), "time": time.time() - t0, "success": success, "seed": seed,
+            "solution": _cfg_list(solution), "info": best}
 
 
 def gradient_free_traj_optimize(robot, dist_est, start_cfg, target_cfg, options):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 3
+#define DC_ABI_VERSION 4
 
 #define DC_MAX_DOF 16
 #define DC_MAX_LINKS 16
@@ -90,6 +90,11 @@ typedef struct dc_fk_desc {
   int32_t n_arms;
   int32_t n_keypoints;
   int32_t n_links;
+  int32_t n_repeat;   /* > 1: the map is applied to n_repeat consecutive blocks of (dof - time_last)/n_repeat columns and the
+                         features are concatenated (LineFKKernel, kernel.py:145-173: a path segment's two end configurations
+                         side by side); n_points * point_dim is then the TOTAL feature count and point_dim = 1 */
+  int32_t time_last;  /* 1: the last column of q is a time stamp passed through as the last feature (TemporalFKKernel,
+                         kernel.py:175-202) */
   int32_t reserved;
   double link_length[DC_MAX_LINKS];
   double keypoints[3][DC_MAX_KEYPOINTS]; /* body-frame key points, row r = coordinate r */
@@ -100,13 +105,19 @@ typedef struct dc_fk_desc {
 typedef enum dc_kernel_kind {
   DC_K_RQ = 1,           /* RQKernel      kernel.py:12-29   k = (1 + gamma/p r^2)^-p   param=gamma order=p */
   DC_K_POLYHARMONIC = 2, /* Polyharmonic  kernel.py:59-79   k = r^k/eps | r^k log r/eps param=eps   order=k */
-  DC_K_MULTIQUADRIC = 3  /* MultiQuadratic kernel.py:45-57  k = sqrt(r^2/eps^2 + 1)    param=eps          */
+  DC_K_MULTIQUADRIC = 3, /* MultiQuadratic kernel.py:45-57  k = sqrt(r^2/eps^2 + 1)    param=eps          */
+  DC_K_RQ_TEMPORAL = 4   /* TemporalFKKernel kernel.py:175-202: the LAST feature is time;
+                            k = RQ(param, order)(|dx|^2 over the first F-1 features) * RQ(param2, order2)(dt^2) ^ alpha */
 } dc_kernel_kind;
 
 typedef struct dc_kernel_desc {
   int32_t kind;
   int32_t order;
   double param;
+  double param2; /* DC_K_RQ_TEMPORAL: gamma of the time kernel */
+  double alpha;  /* DC_K_RQ_TEMPORAL: exponent of the time kernel */
+  int32_t order2; /* DC_K_RQ_TEMPORAL: p of the time kernel */
+  int32_t reserved;
 } dc_kernel_desc;
 
 /* Support set packed for the fused kernels: row n = [-s_n[0..F) zero-padded to f_pad | w[n,0..C) zero-padded to 1 or a

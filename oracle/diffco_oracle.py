@@ -43,6 +43,37 @@ def rq_kernel(xs, x_primes, gamma: float, p: int = 2):
     return k.squeeze(0) if k.shape[0] == 1 else k
 
 
+def temporal_fk_kernel(xs, x_primes, fkine, gamma, p, gamma_t, p_t, alpha):
+    """TemporalFKKernel.__call__, kernel.py:182-195: rows are [q | t]; rq(FK(q), FK(q')) * t_rq(t, t') ** alpha."""
+    if xs.ndim == 1:
+        xs = xs[None, :]
+    xc = fkine(xs[:, :-1]).reshape(len(xs), -1)
+    sc = fkine(x_primes[:, :-1]).reshape(len(x_primes), -1)
+    return rq_kernel(xc, sc, gamma, p) * rq_kernel(xs[:, -1:], x_primes[:, -1:], gamma_t, p_t) ** alpha
+
+
+def line_fk_kernel(xs, x_primes, fkine, gamma, p: int = 2):
+    """LineFKKernel.__call__, kernel.py:209-220: rows are [q_a | q_b]; rq on the concatenated features of both ends."""
+    if xs.ndim == 1:
+        xs = xs[None, :]
+    if x_primes.ndim == 1:
+        x_primes = x_primes[None, :]
+    dof = xs.shape[1] // 2
+    xc = fkine(xs.reshape(-1, dof)).reshape(len(xs), -1)
+    sc = fkine(x_primes.reshape(-1, dof)).reshape(len(x_primes), -1)
+    return rq_kernel(xc, sc, gamma, p)
+
+
+def line_kernel(xs, x_primes, point_kernel):
+    """LineKernel.__call__, kernel.py:197-207: mean of the point kernel on the two halves of [q_a | q_b] rows."""
+    if xs.ndim == 1:
+        xs = xs[None, :]
+    if x_primes.ndim == 1:
+        x_primes = x_primes[None, :]
+    dof = xs.shape[1] // 2
+    return (point_kernel(xs[:, :dof], x_primes[:, :dof]) + point_kernel(xs[:, dof:], x_primes[:, dof:])) / 2
+
+
 def polyharmonic_kernel(xs, x_primes, k: int, epsilon: float):
     """Polyharmonic.__call__, kernel.py:59-79: r^k/eps (k odd) or r^k log r/eps with NaN->0 (k even); never squeezed."""
     a = _flat_rows(xs, x_primes)

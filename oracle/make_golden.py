@@ -381,13 +381,52 @@ def gen_checkers(ns):
     np.savez_compressed(os.path.join(OUT, "checkers.npz"), **out)
 
 
+def gen_line_temporal(ns):
+    """TemporalFKKernel / LineFKKernel / LineKernel (kernel.py:145-202) on the 7-link planar arm: kernel matrices and the
+    autograd gradient of sum_n w_n k(x, s_n) w.r.t. the raw rows ([q | t] resp. [q_a | q_b])."""
+    K, M = ns.kernel, ns.model
+    g = torch.Generator().manual_seed(41)
+    robot = M.RevolutePlanarRobot(1.0, 0.3, 7)
+    fk = lambda q: robot.fkine(q)
+    out = {}
+    # temporal: rows [q (7) | t]
+    x = torch.cat([(torch.rand(9, 7, generator=g, dtype=torch.float64) * 2 - 1) * np.pi, torch.rand(9, 1, generator=g, dtype=torch.float64)], 1)
+    s = torch.cat([(torch.rand(33, 7, generator=g, dtype=torch.float64) * 2 - 1) * np.pi, torch.rand(33, 1, generator=g, dtype=torch.float64)], 1)
+    s[4] = x[2]
+    s[5, :7] = x[3, :7]  # same configuration, different time
+    w = torch.randn(33, generator=g, dtype=torch.float64)
+    out.update(t_x=_np(x), t_s=_np(s), w=_np(w))
+    for name, (gx, px, gt, pt, al) in {"t_a": (10.0, 2, 5.0, 2, 0.5), "t_b": (3.0, 1, 20.0, 3, 2.0)}.items():
+        k = K.TemporalFKKernel(fk, K.RQKernel(gx, px), K.RQKernel(gt, pt), alpha=al)
+        xv = x.clone().requires_grad_(True)
+        km = k(xv, s)
+        (km @ w).sum().backward()
+        out[name + "_params"] = np.array([gx, px, gt, pt, al])
+        out[name + "_K"] = _np(km)
+        out[name + "_grad"] = _np(xv.grad)
+        out[name + "_K_single"] = _np(k(x[0], s))
+    # line: rows [q_a | q_b]
+    xl = (torch.rand(9, 14, generator=g, dtype=torch.float64) * 2 - 1) * np.pi
+    sl = (torch.rand(33, 14, generator=g, dtype=torch.float64) * 2 - 1) * np.pi
+    sl[7] = xl[1]
+    out.update(l_x=_np(xl), l_s=_np(sl))
+    k = K.LineFKKernel(fk, K.RQKernel(10.0))
+    xv = xl.clone().requires_grad_(True)
+    km = k(xv, sl)
+    (km @ w).sum().backward()
+    out.update(l_K=_np(km), l_grad=_np(xv.grad), l_K_single=_np(k(xl[0], sl)))
+    lk = K.LineKernel(K.RQKernel(2.0))
+    out["lk_K"] = _np(lk(xl, sl))
+    np.savez_compressed(os.path.join(OUT, "line_temporal.npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(4)
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load_legacy()
     only = sys.argv[1:]
-    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay, gen_weighted, gen_checkers):
+    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay, gen_weighted, gen_checkers, gen_line_temporal):
         if only and fn.__name__ not in only:
             continue
         fn(ns)

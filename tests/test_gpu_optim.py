@@ -53,6 +53,36 @@ def test_givengrad_traj_optimize_on_cuda_matches_reference(problem):
     assert abs(rec["cost"] - float(g["slsqp_cost"])) <= 1e-4 * max(1.0, abs(float(g["slsqp_cost"])))
 
 
+def test_trustconstr_on_cuda_hessian_and_record(problem):
+    """optim.py:324-507 on the CUDA dist_est: the finite-difference constraint Hessian (one fused launch over all perturbed
+    paths) against the double backward of the float64 oracle on the same model, then a short trust-constr run."""
+    from diffco_b200 import optim as OPT
+    from oracle import diffco_oracle as O
+
+    g, robot, dc, start, target, init, opts = problem
+    path = init.clone()
+    path[1:-1] += 0.3 * torch.randn(10, 7, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    x = path[1:-1].reshape(-1).numpy()
+    prob = OPT._SlsqpProblem(robot, dc.poly_score, path, -0.3, 0.6)
+    v = torch.randn(11, generator=torch.Generator().manual_seed(4), dtype=torch.float64)
+    got = prob.hess_con_collision(x, v.numpy())
+    fk = lambda q: O.fk_planar_chain(q, torch.ones(7, dtype=torch.float64))
+    St, nodes = fk(dc.support_points.double().cpu()), dc.rbf_nodes.double().cpu().reshape(-1)
+    ref_est = lambda p: O.poly_score(p, fk, O.KernelSpec("polyharmonic", 1.0, 1), St, nodes)
+    ref = OPT._SlsqpProblem(robot, ref_est, path, -0.3, 0.6)
+    want = torch.autograd.functional.hessian(lambda p: torch.dot(ref.collision_tensor(p), v), ref.full_path(x).detach())
+    want = want[1:-1, :, 1:-1, :].reshape(70, 70).numpy()
+    assert np.abs(want).max() > 0
+    assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()
+    o = dict(opts, MAXITER=10, extra_optimizer_options={"verbose": 0}, init_solution=init.clone())
+    rec = OPT.trustconstr_traj_optimize(robot, dc.poly_score, start, target, o)
+    sol = torch.tensor(rec["solution"], dtype=torch.float64)
+    assert sol.shape == init.shape and torch.equal(sol[0], start) and torch.equal(sol[-1], target)
+    before = -prob.con_collision(init[1:-1].reshape(-1).numpy()).sum()
+    after = -prob.con_collision(sol[1:-1].reshape(-1).numpy()).sum()
+    assert after <= before + 1e-9 and rec["cnt_check"] > 0
+
+
 def test_weighted_step_device_resident(problem):
     """Weighted.step (optim.py:686-761) with the waypoints on the GPU: autograd path vs the same loop on the oracle."""
     from diffco_b200 import optim as OPT

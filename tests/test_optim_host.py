@@ -77,9 +77,39 @@ def test_two_point_initial_solution_short_circuits():
 
 def test_unsupported_optimisers_fail_loudly():
     with pytest.raises(NotImplementedError):
-        OPT.trustconstr_traj_optimize(None, None, None, None, {})
-    with pytest.raises(NotImplementedError):
         OPT.gradient_free_traj_optimize(None, None, None, None, {})
+
+
+def test_constraint_hessian_matches_double_backward():
+    """optim.py:380-391: the reference gets sum_k v_k Hessian(c_k) by a double backward through its autograd kernel; ours
+    is a central difference of the analytic first derivative, all perturbed paths in one dist_est call.  Same matrix."""
+    g, robot, dist_est, start, target, init, opts = golden_problem()
+    path = init.clone()
+    path[1:-1] += 0.3 * torch.randn(10, 7, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    prob = OPT._SlsqpProblem(robot, dist_est, path, -0.3, 0.6)
+    x = path[1:-1].reshape(-1).numpy()
+    assert (prob.con_collision(x) < 0).any(), "the test path must violate the constraint somewhere"
+    v = torch.randn(11, generator=torch.Generator().manual_seed(4), dtype=torch.float64)
+    got = prob.hess_con_collision(x, v.numpy(), fd_step=1e-5)
+    full = prob.full_path(x).detach()
+    want = torch.autograd.functional.hessian(lambda p: torch.dot(prob.collision_tensor(p), v), full, vectorize=False)
+    want = want[1:-1, :, 1:-1, :].reshape(70, 70).numpy()
+    assert got.shape == (70, 70) and np.abs(want).max() > 0
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    assert np.allclose(prob.hess_con_collision(x, np.zeros(11)), 0)
+
+
+def test_trustconstr_traj_optimize_runs_and_reduces_violation():
+    g, robot, dist_est, start, target, init, opts = golden_problem()
+    opts = dict(opts, MAXITER=12, extra_optimizer_options={"verbose": 0}, init_solution=init.clone(), hess_fd_step=1e-5)
+    rec = OPT.trustconstr_traj_optimize(robot, dist_est, start, target, opts)
+    assert set(rec) == {"start_cfg", "target_cfg", "cnt_check", "cost", "time", "success", "seed", "solution", "info"}
+    sol = torch.tensor(rec["solution"], dtype=torch.float64)
+    assert sol.shape == init.shape and torch.equal(sol[0], start) and torch.equal(sol[-1], target) and rec["cnt_check"] > 0
+    prob = OPT._SlsqpProblem(robot, dist_est, init, -0.3, 0.6)
+    before = -prob.con_collision(init[1:-1].reshape(-1).numpy()).sum()
+    after = -prob.con_collision(sol[1:-1].reshape(-1).numpy()).sum()
+    assert after <= before
 
 
 def test_weighted_step_autograd_path_with_stub_checker():

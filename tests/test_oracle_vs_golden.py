@@ -305,3 +305,28 @@ def test_checker_fit_update_verify_match_reference():
     close((O.poly_score(Q, fk, ph, perc2.support_transformed, perc2.rbf_nodes) + bias2).numpy(), g["upd_collision_score"], 1e-7)
     lab_q = 2 * (P.circle_labels(robot, Q) > 0).double() - 1
     close(np.array([float(v) for v in O.checker_rates(perc2, fk, Q, lab_q, bias2)]), g["upd_verify_rates"], 1e-6)
+
+
+def test_line_and_temporal_kernels_match_reference():
+    """kernel.py:145-202 (TemporalFKKernel, LineKernel, LineFKKernel) — restatement vs the reference's matrices and the
+    autograd gradient of sum_n w_n k(x, s_n) w.r.t. the raw rows."""
+    g = load("line_temporal.npz")
+    fk = lambda q: O.fk_planar_chain(q, torch.ones(7, dtype=torch.float64))
+    w = T64(g["w"])
+    x, s = T64(g["t_x"]), T64(g["t_s"])
+    for name in ("t_a", "t_b"):
+        gx, px, gt, pt, al = g[name + "_params"]
+        xv = x.clone().requires_grad_(True)
+        km = O.temporal_fk_kernel(xv, s, fk, gx, int(px), gt, int(pt), al)
+        (km @ w).sum().backward()
+        close(km.detach(), g[name + "_K"])
+        close(xv.grad, g[name + "_grad"], 1e-11)
+        close(O.temporal_fk_kernel(x[0], s, fk, gx, int(px), gt, int(pt), al), g[name + "_K_single"])
+    xl, sl = T64(g["l_x"]), T64(g["l_s"])
+    xv = xl.clone().requires_grad_(True)
+    km = O.line_fk_kernel(xv, sl, fk, 10.0)
+    (km @ w).sum().backward()
+    close(km.detach(), g["l_K"])
+    close(xv.grad, g["l_grad"], 1e-11)
+    close(O.line_fk_kernel(xl[0], sl, fk, 10.0), g["l_K_single"])
+    close(O.line_kernel(xl, sl, lambda a, b: O.rq_kernel(a, b, 2.0)), g["lk_K"])
