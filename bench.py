@@ -261,6 +261,8 @@ def run_native(args):
 
     lib = _lib.load()
     _lib.check(lib.dc_set_option(_lib.DC_OPT_TC_ENABLE, float(args.tc)), "dc_set_option")
+    # the pinned buffers of the host path are allocated below: put them on this GPU's memory node
+    numa_cpus = D.bind_host_thread_to_gpu(visible_index(local)) if world > 1 else None
     group = dist.group.WORLD if world > 1 else None
     B = args.batch
     S, w, q = make_problem(rank, B)
@@ -427,6 +429,8 @@ def run_native(args):
             "roofline_compute": roofline_compute,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": q_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
+                    "host_numa": (f"rank 0 pinned to {len(numa_cpus)} GPU-local CPUs before allocating its pinned buffers"
+                                  if numa_cpus else "not bound"),
                     "path": ("one launch per rank: the kernel reads the pinned q and writes this rank's records to the pinned "
                              "output (zero-copy over PCIe)" + (" and to every peer's gathered buffer" if world > 1 and fused_ag else "")
                              if which == 2 else "dc_score_grad_host")},

@@ -18,11 +18,13 @@ DC_MAX_ARMS = 2
 DC_MAX_ARM_JOINTS = 8
 DC_MAX_TOOL_POINTS = 2
 DC_MAX_FEATURES = 64
+DC_MAX_TREE_NODES = 24
 DC_MAX_CLASSES = 8
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 DC_F32, DC_F64 = 0, 1
-DC_FK_NONE, DC_FK_PLANAR_CHAIN, DC_FK_SE2_BODY, DC_FK_SE3_BODY, DC_FK_DH_ARMS, DC_FK_SE2_BASE_PLANAR_ARM = range(6)
+DC_FK_NONE, DC_FK_PLANAR_CHAIN, DC_FK_SE2_BODY, DC_FK_SE3_BODY, DC_FK_DH_ARMS, DC_FK_SE2_BASE_PLANAR_ARM, DC_FK_JOINT_TREE = range(7)
+DC_JOINT_FIXED, DC_JOINT_REV_X, DC_JOINT_REV_Y, DC_JOINT_REV_Z, DC_JOINT_PRISMATIC = range(5)
 DC_K_RQ, DC_K_POLYHARMONIC, DC_K_MULTIQUADRIC, DC_K_RQ_TEMPORAL = 1, 2, 3, 4
 DC_GRAD_NONE, DC_GRAD_SUM, DC_GRAD_JAC = 0, 1, 2
 
@@ -45,6 +47,20 @@ class DhArm(C.Structure):
     ]
 
 
+class TreeNode(C.Structure):
+    _fields_ = [
+        ("parent", C.c_int32),
+        ("q_index", C.c_int32),
+        ("joint", C.c_int32),
+        ("out_slot", C.c_int32),
+        ("rot", C.c_double * 9),
+        ("trans", C.c_double * 3),
+        ("axis", C.c_double * 3),
+        ("mimic_mul", C.c_double),
+        ("mimic_off", C.c_double),
+    ]
+
+
 class FkDesc(C.Structure):
     _fields_ = [
         ("type", C.c_int32),
@@ -56,10 +72,11 @@ class FkDesc(C.Structure):
         ("n_links", C.c_int32),
         ("n_repeat", C.c_int32),
         ("time_last", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_nodes", C.c_int32),
         ("link_length", C.c_double * DC_MAX_LINKS),
         ("keypoints", (C.c_double * DC_MAX_KEYPOINTS) * 3),
         ("arms", DhArm * DC_MAX_ARMS),
+        ("tree", TreeNode * DC_MAX_TREE_NODES),
     ]
 
     @property
@@ -164,6 +181,7 @@ PROTOTYPES = {
                                   C.POINTER(TrajDense), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_void_p]),
     "dc_fk_vjp": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dc_fk_tree_frames": (C.c_int, [C.POINTER(FkDesc), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -8,9 +8,10 @@ the support points + uniform samples, jump-start training, :220-252), ``verify``
 ``normalizer`` / ``unnormalizer``.  All arithmetic runs in libdiffco_b200: training is one persistent CUDA launch,
 scoring one fused launch.
 
-What differs, and why: the reference builds the robot from a URDF (yourdfpy + trimesh) and the ground truth from
-python-fcl / cuRobo / MoveIt — none of which is part of the hot path or installed here.  The robot is therefore one of
-this package's ``model`` robots (``fkine`` is fused into the kernels) and the geometric ground truth is INJECTED through
+What differs, and why: the reference takes the ground truth from python-fcl / cuRobo / MoveIt on the URDF's meshes — none of
+which is part of the hot path or installed here.  The robot is a URDF path / ``collision_interfaces.URDFRobot`` (kinematic
+tree compiled into a joint program) or one of this package's ``model`` robots — either way ``fkine`` is fused into the
+kernels — and the geometric ground truth is INJECTED through
 ``gt_check_func(q) -> (B,) {0, 1}`` — an argument the reference's constructor already has (collision_checkers.py:46,87-88).
 """
 from __future__ import annotations
@@ -48,11 +49,15 @@ class CollisionChecker:
 
     def __init__(self, robot=None, robot_base_transform=None, environment=None, robot_topic=None, planning_scene_topic=None,
                  gt_check_func: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, device="cuda") -> None:
-        if isinstance(robot, str) or robot_topic is not None or planning_scene_topic is not None:
-            raise NotImplementedError("URDF / ROS robots need yourdfpy, trimesh, python-fcl or MoveIt (outside the hot path): pass a "
+        if robot_topic is not None or planning_scene_topic is not None:
+            raise NotImplementedError("ROS / MoveIt robots are outside this package: pass a URDF path, a URDFRobot or a "
                                       "diffco_b200.model robot")
+        if isinstance(robot, str):  # collision_checkers.py:52-56: a path to a URDF file
+            from .collision_interfaces import URDFRobot
+
+            robot = URDFRobot(robot, base_transform=robot_base_transform, device=device)
         if robot is None or not hasattr(robot, "fkine") or not hasattr(robot, "limits"):
-            raise TypeError("robot must be a diffco_b200.model robot (dof, limits, fkine)")
+            raise TypeError("robot must be a URDF path, a URDFRobot or a diffco_b200.model robot (dof, limits, fkine)")
         if gt_check_func is None:
             raise NotImplementedError("the geometric ground truth (python-fcl in the reference) is not part of this package: "
                                       "pass gt_check_func(q) -> (B,) labels in {0, 1}")

@@ -108,6 +108,16 @@ static bool fk_valid(const dc_fk_desc& fk) {
       }
       return true;
     }
+    case DC_FK_JOINT_TREE: {
+      if (fin % 3 || !points(3, fin / 3) || fk.n_nodes < 1 || fk.n_nodes > DC_MAX_TREE_NODES) return false;
+      for (int i = 0; i < fk.n_nodes; ++i) {
+        const dc_tree_node& nd = fk.tree[i];
+        if (nd.parent >= i || nd.parent < -1 || nd.q_index >= din || nd.q_index < -1) return false;
+        if (nd.joint < DC_JOINT_FIXED || nd.joint > DC_JOINT_PRISMATIC || nd.out_slot >= fin / 3 || nd.out_slot < -1) return false;
+        if (nd.joint == DC_JOINT_FIXED && nd.q_index >= 0) return false;
+      }
+      return true;
+    }
     default:
       return false;
   }
@@ -172,6 +182,22 @@ __global__ void __launch_bounds__(128) fk_forward_kernel(const __grid_constant__
 #pragma unroll
   for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < fk.dof) ? q[b * fk.dof + i] : (T)0;
   fk_features(fk, qv, x + b * F, 1);  // float32: evaluated in float64 and rounded once (dc_fk.cuh)
+}
+
+// [R | t] of every body of a joint tree (float32: evaluated in float64, rounded once, like the features)
+template <typename T>
+__global__ void __launch_bounds__(128) fk_tree_frames_kernel(const __grid_constant__ dc_fk_desc fk, const T* __restrict__ q,
+                                                             long long batch, T* __restrict__ out) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  double qv[DC_MAX_DOF];
+#pragma unroll
+  for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (i < fk.dof) ? (double)q[b * fk.dof + i] : 0.0;
+  double fr[DC_MAX_TREE_NODES][12];
+  fk_tree_frames<double>(fk, qv, fr);
+  T* o = out + b * fk.n_nodes * 12;
+  for (int i = 0; i < fk.n_nodes; ++i)
+    for (int e = 0; e < 12; ++e) o[i * 12 + e] = (T)fr[i][e];
 }
 
 // float32 features as (hi, lo) pairs: x = hi + lo to ~1e-9 (hi is what fk_forward_kernel<float> returns)
@@ -477,6 +503,20 @@ int dc_pack_supports_lo(const void* s_lo, int64_t n, int32_t n_features, int32_t
   const long long total = (long long)n * row;
   pack_supports_lo_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)s_lo, n, n_features, row,
                                                                                         (float*)table_lo);
+  DC_LAUNCH_CHECK();
+  return DC_OK;
+}
+
+int dc_fk_tree_frames(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, void* frames, dc_stream_t stream) {
+  if (!fk || !fk_valid(*fk) || fk->type != DC_FK_JOINT_TREE || fk->n_repeat > 1 || fk->time_last) return DC_ERR_INVALID_ARG;
+  if (batch < 0 || (dtype != DC_F32 && dtype != DC_F64)) return DC_ERR_INVALID_ARG;
+  if (batch == 0) return DC_OK;
+  if (!q || !frames) return DC_ERR_INVALID_ARG;
+  const unsigned grid = (unsigned)((batch + 127) / 128);
+  if (dtype == DC_F32)
+    fk_tree_frames_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(*fk, (const float*)q, batch, (float*)frames);
+  else
+    fk_tree_frames_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(*fk, (const double*)q, batch, (double*)frames);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -243,6 +243,118 @@ __device__ void fk_dh_arm_vjp(const dc_dh_arm& arm, const T* q, Strided<T> x, St
   }
 }
 
+// ---- URDF joint tree (collision_interfaces/rigid_body.py:86-141, urdf_interface.py:517-553) ------------------------
+// Frames of all bodies, parents first: fr[i] = row-major [R | t] (12 values).
+template <typename T>
+__device__ void fk_tree_frames(const dc_fk_desc& fk, const T* q, T (*fr)[12]) {
+  for (int i = 0; i < fk.n_nodes; ++i) {
+    const dc_tree_node& nd = fk.tree[i];
+    T Rp[9] = {(T)1, (T)0, (T)0, (T)0, (T)1, (T)0, (T)0, (T)0, (T)1}, tp[3] = {(T)0, (T)0, (T)0};
+    if (nd.parent >= 0) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rp[e] = fr[nd.parent][e];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) tp[e] = fr[nd.parent][9 + e];
+    }
+    const T qv = nd.q_index >= 0 ? (T)nd.mimic_mul * q[nd.q_index] + (T)nd.mimic_off : (T)0;
+    // A = R_parent * rot
+    T A[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        A[3 * r + c] = Rp[3 * r] * (T)nd.rot[c] + Rp[3 * r + 1] * (T)nd.rot[3 + c] + Rp[3 * r + 2] * (T)nd.rot[6 + c];
+    T tj[3] = {(T)nd.trans[0], (T)nd.trans[1], (T)nd.trans[2]};
+    T* o = fr[i];
+    if (nd.joint >= DC_JOINT_REV_X && nd.joint <= DC_JOINT_REV_Z) {
+      T sn, cs;
+      sincos_t((T)nd.axis[0] * qv, &sn, &cs);
+      // A * Rot_k(angle): the two columns other than k mix; (u, v) = the next two axes in cyclic order
+      const int k = nd.joint - DC_JOINT_REV_X, u = (k + 1) % 3, v = (k + 2) % 3;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const T au = A[3 * r + u], av = A[3 * r + v];
+        o[3 * r + k] = A[3 * r + k];
+        o[3 * r + u] = au * cs + av * sn;
+        o[3 * r + v] = av * cs - au * sn;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) o[e] = A[e];
+      if (nd.joint == DC_JOINT_PRISMATIC) {
+        // trans + rot * axis * q'
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          tj[r] += ((T)nd.rot[3 * r] * (T)nd.axis[0] + (T)nd.rot[3 * r + 1] * (T)nd.axis[1] + (T)nd.rot[3 * r + 2] * (T)nd.axis[2]) * qv;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o[9 + r] = tp[r] + Rp[3 * r] * tj[0] + Rp[3 * r + 1] * tj[1] + Rp[3 * r + 2] * tj[2];
+  }
+}
+
+template <typename T>
+__device__ __noinline__ void fk_tree_fwd(const dc_fk_desc& fk, const T* q, Strided<T> x) {
+  T fr[DC_MAX_TREE_NODES][12];
+  fk_tree_frames<T>(fk, q, fr);
+  for (int i = 0; i < fk.n_nodes; ++i) {
+    const int slot = fk.tree[i].out_slot;
+    if (slot >= 0) {
+      x[3 * slot] = fr[i][9];
+      x[3 * slot + 1] = fr[i][10];
+      x[3 * slot + 2] = fr[i][11];
+    }
+  }
+}
+
+// gq = J^T g.  With F_i / M_i the sums of g_l and p_l x g_l over the bodies l of subtree(i):
+//   revolute:  d p_l / d q' = a_i x (p_l - t_i),  a_i = sign * column k of R_i   ->  gq' = a_i . (M_i - t_i x F_i)
+//   prismatic: d p_l / d q' = R_i axis                                           ->  gq' = (R_i axis) . F_i
+template <typename T>
+__device__ __noinline__ void fk_tree_vjp(const dc_fk_desc& fk, const T* q, Strided<T> g, T* gq) {
+  T fr[DC_MAX_TREE_NODES][12];
+  T acc[DC_MAX_TREE_NODES][6];
+  fk_tree_frames<T>(fk, q, fr);
+  for (int i = 0; i < fk.n_nodes; ++i) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) acc[i][e] = (T)0;
+    if (fk.tree[i].q_index >= 0) gq[fk.tree[i].q_index] = (T)0;
+  }
+  for (int i = fk.n_nodes - 1; i >= 0; --i) {
+    const dc_tree_node& nd = fk.tree[i];
+    const T* f = fr[i];
+    if (nd.out_slot >= 0) {
+      const T gx = g[3 * nd.out_slot], gy = g[3 * nd.out_slot + 1], gz = g[3 * nd.out_slot + 2];
+      acc[i][0] += gx;
+      acc[i][1] += gy;
+      acc[i][2] += gz;
+      acc[i][3] += f[10] * gz - f[11] * gy;
+      acc[i][4] += f[11] * gx - f[9] * gz;
+      acc[i][5] += f[9] * gy - f[10] * gx;
+    }
+    if (nd.q_index >= 0) {
+      T d = (T)0;
+      if (nd.joint == DC_JOINT_PRISMATIC) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          d += (f[3 * r] * (T)nd.axis[0] + f[3 * r + 1] * (T)nd.axis[1] + f[3 * r + 2] * (T)nd.axis[2]) * acc[i][r];
+      } else if (nd.joint != DC_JOINT_FIXED) {
+        const int k = nd.joint - DC_JOINT_REV_X;
+        const T ax = f[k], ay = f[3 + k], az = f[6 + k];
+        const T mx = acc[i][3] - (f[10] * acc[i][2] - f[11] * acc[i][1]);
+        const T my = acc[i][4] - (f[11] * acc[i][0] - f[9] * acc[i][2]);
+        const T mz = acc[i][5] - (f[9] * acc[i][1] - f[10] * acc[i][0]);
+        d = (T)nd.axis[0] * (ax * mx + ay * my + az * mz);
+      }
+      gq[nd.q_index] += (T)nd.mimic_mul * d;
+    }
+    if (nd.parent >= 0) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[nd.parent][e] += acc[i][e];
+    }
+  }
+}
+
 // ---- dispatch ----------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void fk_forward_one(const dc_fk_desc& fk, const T* q, T* xp, int ld) {
@@ -270,6 +382,9 @@ __device__ __forceinline__ void fk_forward_one(const dc_fk_desc& fk, const T* q,
       fk_planar_fwd<T>(fk.link_length, fk.n_links, q + 3, xa, q[0], q[1], q[2]);
       break;
     }
+    case DC_FK_JOINT_TREE:
+      fk_tree_fwd<T>(fk, q, x);
+      break;
     default:
       break;
   }
@@ -414,6 +529,9 @@ __device__ __forceinline__ void fk_vjp_one(const dc_fk_desc& fk, const T* q, T* 
       fk_planar_vjp<T>(fk.n_links, xa, ga, q[0], q[1], gq + 3);
       break;
     }
+    case DC_FK_JOINT_TREE:
+      fk_tree_vjp<T>(fk, q, g, gq);
+      break;
     default:
       break;
   }

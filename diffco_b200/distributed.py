@@ -22,6 +22,34 @@ from . import _lib, functional
 from ._lib import DC_GRAD_SUM
 
 
+def bind_host_thread_to_gpu(device_index: int) -> Optional[list]:
+    """Pin the calling thread to the CPUs that are NUMA-local to GPU ``device_index`` (physical index, i.e. after
+    CUDA_VISIBLE_DEVICES), so that pinned host buffers allocated afterwards land on that GPU's memory node (first touch).
+    The zero-copy host path (``score_and_grad_host``) moves every query and record over PCIe inside the kernel; with eight
+    ranks on a two-socket box, buffers on the wrong socket halve its throughput.  Returns the CPU list, or None when the
+    topology cannot be read (then nothing is changed)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        with open(f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = []
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int, int]:
     """Contiguous balanced partition: (lo, hi, rows_per_rank) with rows_per_rank = ceil(total / world); the last
     ranks may own fewer (or zero) real rows and are padded up to rows_per_rank for the equal-size all-gather."""

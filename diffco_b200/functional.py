@@ -217,6 +217,21 @@ def fk_vjp(fk: FkDesc, q: torch.Tensor, g_x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def fk_tree_frames(fk: FkDesc, q: torch.Tensor) -> torch.Tensor:
+    """(B, n_nodes, 12): row-major [R | t] of every body of a DC_FK_JOINT_TREE map; computed on the GPU, returned where
+    ``q`` lives."""
+    lib = _lib.load()
+    dev = q.device if q.is_cuda else _require_cuda()
+    dtype = q.dtype if q.dtype in (torch.float32, torch.float64) else torch.float32
+    qd = q.detach().to(device=dev, dtype=dtype).reshape(-1, fk.dof).contiguous()
+    out = torch.empty((qd.shape[0], fk.n_nodes, 12), dtype=dtype, device=dev)
+    if qd.shape[0]:
+        with torch.cuda.device(dev):
+            _lib.check(lib.dc_fk_tree_frames(C.byref(fk), qd.data_ptr(), qd.shape[0], _dtype_code(dtype), out.data_ptr(),
+                                             _stream_ptr(dev)), "dc_fk_tree_frames")
+    return out.to(q.device)
+
+
 # --------------------------------------------------------------------------------------------------------
 # autograd
 # --------------------------------------------------------------------------------------------------------

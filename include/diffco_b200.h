@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 4
+#define DC_ABI_VERSION 5
 
 #define DC_MAX_DOF 16
 #define DC_MAX_LINKS 16
@@ -41,6 +41,7 @@ extern "C" {
 #define DC_MAX_ARM_JOINTS 8
 #define DC_MAX_TOOL_POINTS 2
 #define DC_MAX_FEATURES 64
+#define DC_MAX_TREE_NODES 24
 #define DC_MAX_CLASSES 8
 
 typedef struct CUstream_st* dc_stream_t; /* == cudaStream_t */
@@ -62,7 +63,9 @@ typedef enum dc_fk_type {
   DC_FK_SE2_BODY = 2,           /* RigidPlanarBody.fkine               model.py:90-93                   */
   DC_FK_SE3_BODY = 3,           /* RigidBody.fkine                     model.py:156-159                 */
   DC_FK_DH_ARMS = 4,            /* Baxter L/R/dual, Panda, DualPanda   model.py:225-241,366-383,430-503 */
-  DC_FK_SE2_BASE_PLANAR_ARM = 5 /* SE(2) base carrying a planar chain  (BASELINE.json configs[3])       */
+  DC_FK_SE2_BASE_PLANAR_ARM = 5, /* SE(2) base carrying a planar chain  (BASELINE.json configs[3])       */
+  DC_FK_JOINT_TREE = 6          /* URDF kinematic tree: URDFRobot.compute_forward_kinematics_all_links,
+                                   collision_interfaces/urdf_interface.py:517-553 + rigid_body.py:86-141 */
 } dc_fk_type;
 
 /* One serial standard-DH arm (utils.DH2mat, diffco/utils.py:66-77). */
@@ -82,6 +85,23 @@ typedef struct dc_dh_arm {
   double tool[DC_MAX_TOOL_POINTS][3];
 } dc_dh_arm;
 
+/* One body of a URDF tree with the joint that attaches it to its parent (rigid_body.py:86-141).  Bodies are listed
+ * parents first.  Frame of body i:  R_i = R_parent rot Rot(q'),  t_i = t_parent + R_parent trans   (revolute / continuous)
+ *                                   R_i = R_parent rot,          t_i = t_parent + R_parent (trans + rot axis q')  (prismatic)
+ * with q' = mimic_mul * q[q_index] + mimic_off (q_index < 0: fixed joint, q' = 0). */
+typedef enum dc_joint_kind { DC_JOINT_FIXED = 0, DC_JOINT_REV_X = 1, DC_JOINT_REV_Y = 2, DC_JOINT_REV_Z = 3, DC_JOINT_PRISMATIC = 4 } dc_joint_kind;
+typedef struct dc_tree_node {
+  int32_t parent;   /* index of the parent body, -1 for the root (its rot / trans then hold the robot's base transform) */
+  int32_t q_index;  /* column of q driving the joint, -1 = fixed */
+  int32_t joint;    /* dc_joint_kind */
+  int32_t out_slot; /* output point index of the body frame's origin, or -1 */
+  double rot[9];    /* row-major fixed rotation of the joint origin (rpy) */
+  double trans[3];  /* joint origin translation */
+  double axis[3];   /* prismatic: the axis; revolute: axis[0] = sign applied to q' (rigid_body.py:103-108) */
+  double mimic_mul; /* 1 unless the joint mimics another */
+  double mimic_off;
+} dc_tree_node;
+
 typedef struct dc_fk_desc {
   int32_t type;       /* dc_fk_type */
   int32_t dof;        /* D */
@@ -95,10 +115,11 @@ typedef struct dc_fk_desc {
                          side by side); n_points * point_dim is then the TOTAL feature count and point_dim = 1 */
   int32_t time_last;  /* 1: the last column of q is a time stamp passed through as the last feature (TemporalFKKernel,
                          kernel.py:175-202) */
-  int32_t reserved;
+  int32_t n_nodes;    /* DC_FK_JOINT_TREE: bodies in tree[] */
   double link_length[DC_MAX_LINKS];
   double keypoints[3][DC_MAX_KEYPOINTS]; /* body-frame key points, row r = coordinate r */
   dc_dh_arm arms[DC_MAX_ARMS];
+  dc_tree_node tree[DC_MAX_TREE_NODES];
 } dc_fk_desc;
 
 /* Radial kernels (diffco/kernel.py). */
@@ -221,6 +242,9 @@ int dc_fk_forward_split(const dc_fk_desc* fk, const void* q, int64_t batch, void
 int dc_pack_supports_lo(const void* s_lo, int64_t n, int32_t n_features, int32_t n_class, void* table_lo, dc_stream_t stream);
 int dc_fk_vjp(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, const void* g_x, void* g_q,
               dc_stream_t stream);
+/* DC_FK_JOINT_TREE only: frames[B][n_nodes][12] = row-major [R | t] of every body (what the reference's
+ * compute_forward_kinematics_all_links returns per link, urdf_interface.py:517-553). */
+int dc_fk_tree_frames(const dc_fk_desc* fk, const void* q, int64_t batch, int32_t dtype, void* frames, dc_stream_t stream);
 
 /*
  * Greedy kernel-perceptron training, the whole loop in one launch (DiffCo.train_perceptron,

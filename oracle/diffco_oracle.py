@@ -248,6 +248,36 @@ def fk_se2_base_planar_arm(q, base_keypoints, link_length):
 # --------------------------------------------------------------------------------------------------
 
 
+def fk_joint_tree(q, nodes, n_slots):
+    """Link-frame origins of a URDF tree, (B, n_slots, 3) — RigidBody.forward_kinematics, rigid_body.py:86-141, unrolled over
+    a parents-first node list instead of recursed: each node = dict(parent, q_index, joint in {'fixed', 'x', 'y', 'z',
+    'prismatic'}, sign, axis (3,), rot (3, 3) = Rz(yaw) Ry(pitch) Rx(roll), trans (3,), mimic_mul, mimic_off, out_slot).
+    Revolute: R = R_parent rot Rot_axis(sign q'), t = t_parent + R_parent trans (:101-113); prismatic: R = R_parent rot,
+    t = t_parent + R_parent (trans + rot axis q') (:114-124); q' = q * multiplier + offset for mimic joints (:93-94)."""
+    B = q.shape[0]
+    eye = torch.eye(3, dtype=q.dtype).expand(B, 3, 3)
+    frames = []
+    out = [None] * n_slots
+    for nd in nodes:
+        Rp, tp = (eye, torch.zeros(B, 3, dtype=q.dtype)) if nd["parent"] < 0 else frames[nd["parent"]]
+        rot, trans = nd["rot"].to(q.dtype), nd["trans"].to(q.dtype)
+        qv = q[:, nd["q_index"]] * nd["mimic_mul"] + nd["mimic_off"] if nd["q_index"] >= 0 else torch.zeros(B, dtype=q.dtype)
+        R = Rp @ rot
+        tj = trans.expand(B, 3)
+        if nd["joint"] in ("x", "y", "z"):
+            a = nd["sign"] * qv
+            c, s_, z, o = torch.cos(a), torch.sin(a), torch.zeros_like(a), torch.ones_like(a)
+            rows = {"x": [o, z, z, z, c, -s_, z, s_, c], "y": [c, z, s_, z, o, z, -s_, z, c], "z": [c, -s_, z, s_, c, z, z, z, o]}
+            R = R @ torch.stack(rows[nd["joint"]], dim=1).reshape(B, 3, 3)
+        elif nd["joint"] == "prismatic":
+            tj = tj + (rot @ nd["axis"].to(q.dtype)).expand(B, 3) * qv[:, None]
+        t = tp + (Rp @ tj[:, :, None])[:, :, 0]
+        frames.append((R, t))
+        if nd["out_slot"] >= 0:
+            out[nd["out_slot"]] = t
+    return torch.stack(out, dim=1), frames
+
+
 def score_original(point, transform, kernel, support_transformed, gains):
     """DiffCo.score_original, kernel_perceptrons.py:362-370 (gains (N,) -> (B,) / 0-dim when B==1);
     legacy MultiDiffCo.score, deprecated/MultiDiffCo.py:118-123 (gains (N,C) -> (B,C))."""

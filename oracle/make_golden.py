@@ -420,13 +420,123 @@ def gen_line_temporal(ns):
     np.savez_compressed(os.path.join(OUT, "line_temporal.npz"), **out)
 
 
+def _reference_urdf_tree(path, base=None):
+    """The reference's own RigidBody tree (rigid_body.py, imported unmodified) built the way URDFRobot.__init__ builds it
+    (urdf_interface.py:370-403,556-600) — except that the file is read with xml.etree here because yourdfpy is not
+    installed.  Returns (bodies, fk) with fk(q) -> {link: (translation, rotation)} as
+    compute_forward_kinematics_all_links does (urdf_interface.py:517-553)."""
+    import importlib
+    import types
+    import xml.etree.ElementTree as ET
+
+    if "diffco.collision_interfaces" not in sys.modules or not hasattr(sys.modules["diffco.collision_interfaces"], "__path__"):
+        pkg = types.ModuleType("diffco.collision_interfaces")
+        pkg.__path__ = [os.path.join(ref_loader.REFERENCE_ROOT, "diffco", "collision_interfaces")]
+        sys.modules["diffco.collision_interfaces"] = pkg
+    RB = importlib.import_module("diffco.collision_interfaces.rigid_body")
+    SVA = importlib.import_module("diffco.collision_interfaces.spatial_vector_algebra")
+    root = ET.parse(path).getroot()
+    f3 = lambda el, key: [float(v) for v in el.get(key, "0 0 0").split()]
+    jmap = {j.find("child").get("link"): j for j in root.findall("joint")}
+    jname = {j.get("name"): j for j in root.findall("joint")}
+    bodies, controlled, mimics = [], [], {}
+    for idx, link in enumerate(root.findall("link")):
+        j = jmap.get(link.get("name"))
+        prm = {"link_idx": idx, "link_name": link.get("name"), "joint_limits": None, "joint_mimic": None}
+        if j is None:
+            prm.update(joint_rot_angles=torch.zeros(3), joint_trans=torch.zeros(3), joint_name="base_joint", joint_type="fixed",
+                       joint_axis=torch.zeros((1, 3)))
+        else:
+            o = j.find("origin")
+            prm.update(joint_rot_angles=torch.tensor(f3(o, "rpy") if o is not None else [0.0] * 3, dtype=torch.float32),
+                       joint_trans=torch.tensor(f3(o, "xyz") if o is not None else [0.0] * 3, dtype=torch.float32),
+                       joint_name=j.get("name"), joint_type=j.get("type"), joint_axis=torch.zeros((1, 3)))
+            if j.get("type") != "fixed":
+                ax = j.find("axis")
+                prm["joint_axis"] = torch.tensor(f3(ax, "xyz") if ax is not None else [1.0, 0, 0], dtype=torch.float32).reshape(1, 3)
+                m = j.find("mimic")
+                if m is not None:
+                    prm["joint_mimic"] = types.SimpleNamespace(joint=m.get("joint"), multiplier=float(m.get("multiplier", 1.0)),
+                                                               offset=float(m.get("offset", 0.0)))
+        b = RB.RigidBody(rigid_body_params=prm)
+        if b.joint_type != "fixed":
+            if b.joint_mimic is None:
+                controlled.append(idx)
+            else:
+                mimics.setdefault(jname[b.joint_mimic.joint].find("child").get("link"), []).append(b.name)
+        bodies.append(b)
+    by_name = {b.name: b for b in bodies}
+    for b in bodies:
+        if b.joint_name != "base_joint":
+            parent = by_name[jname[b.joint_name].find("parent").get("link")]
+            b.set_parent(parent)
+            parent.add_child(b)
+    base = torch.eye(4) if base is None else base
+    base_tf = SVA.CoordinateTransform(base[:3, :3], base[:3, 3])
+
+    def fk(q):
+        q_dict = {}
+        for i, bi in enumerate(controlled):
+            q_dict[bodies[bi].name] = q[:, i].unsqueeze(1)
+            for mn in mimics.get(bodies[bi].name, []):
+                q_dict[mn] = q_dict[bodies[bi].name]
+        poses = bodies[0].forward_kinematics(q_dict, False)
+        return {k: base_tf.multiply_transform(v[0]) for k, v in poses.items()}
+
+    return bodies, controlled, fk
+
+
+def gen_urdf(ns):
+    """URDF-tree forward kinematics (rigid_body.py:86-141 via urdf_interface.py:517-553) on the synthetic test URDFs and,
+    for the reference's own Panda description, on the joint program this package compiled from it (the file itself does
+    not travel: the golden holds the compiled dc_fk_desc bytes, q and the reference's outputs).  float32, as the reference
+    computes (its rotation constructors allocate float32)."""
+    import ctypes
+
+    from diffco_b200.collision_interfaces import URDFRobot  # descriptor bytes + feature-link order only
+
+    out = {}
+    cases = {"arm7": (os.path.join(ROOT, "tests", "data", "arm7_gripper.urdf"), None),
+             "torso": (os.path.join(ROOT, "tests", "data", "torso_two_arms.urdf"),
+                       torch.tensor([[0.0, -1.0, 0.0, 0.3], [1.0, 0.0, 0.0, -0.2], [0.0, 0.0, 1.0, 0.1], [0, 0, 0, 1.0]])),
+             "panda": (os.path.join(ref_loader.REFERENCE_ROOT, "diffco", "robot_data", "panda_description", "urdf", "panda.urdf"), None)}
+    g = torch.Generator().manual_seed(77)
+    for name, (path, base) in cases.items():
+        bodies, controlled, fk = _reference_urdf_tree(path, base)
+        lim = torch.zeros(len(controlled), 2)
+        for i, bi in enumerate(controlled):
+            b = bodies[bi]
+            lim[i] = torch.tensor([-np.pi, np.pi]) if b.joint_type != "continuous" else torch.tensor([-2 * np.pi, 2 * np.pi])
+        q = (torch.rand(16, len(controlled), generator=g) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]) * 0.6
+        q[0] = 0
+        unique = [b.name for b in bodies if torch.any(b.joint_trans() != 0)]  # collision_checkers.py:356-358
+        qv = q.clone().requires_grad_(True)
+        poses = fk(qv)
+        feat = torch.stack([poses[n].translation().expand(len(q), 3) for n in unique], dim=-1)  # (B, 3, L): tensorized_fkine_single_robot
+        gx = torch.randn(feat.shape, generator=g)
+        (feat * gx).sum().backward()
+        out[name + "_q"], out[name + "_x"], out[name + "_gx"], out[name + "_gq"] = _np(q), _np(feat), _np(gx), _np(qv.grad)
+        out[name + "_unique"] = np.array(unique)
+        out[name + "_links"] = np.array(list(poses.keys()))
+        # bodies above the first joint come back with batch size 1 (rigid_body.py:126): expand for stacking
+        out[name + "_trans"] = _np(torch.stack([poses[k].translation().expand(len(q), 3) for k in poses], 1))
+        out[name + "_rot"] = _np(torch.stack([poses[k].rotation().expand(len(q), 3, 3) for k in poses], 1))
+        robot = URDFRobot(path, base_transform=base)
+        assert robot.unique_position_link_names == unique, (robot.unique_position_link_names, unique)
+        out[name + "_desc"] = np.frombuffer(bytes(ctypes.string_at(ctypes.addressof(robot.fk_desc), ctypes.sizeof(robot.fk_desc))),
+                                            dtype=np.uint8).copy()
+        out[name + "_nodes"] = np.array(robot.node_names)
+        out[name + "_limits"] = _np(robot.joint_limits)
+    np.savez_compressed(os.path.join(OUT, "urdf.npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(4)
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load_legacy()
     only = sys.argv[1:]
-    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay, gen_weighted, gen_checkers, gen_line_temporal):
+    for fn in (gen_kernels, gen_fk, gen_perceptron, gen_multiclass, gen_optim_replay, gen_weighted, gen_checkers, gen_line_temporal, gen_urdf):
         if only and fn.__name__ not in only:
             continue
         fn(ns)

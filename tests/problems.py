@@ -115,3 +115,17 @@ def rel_to_max(a, b):
     """max|a-b| / max|b| — the parity metric of BASELINE.md §3."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+
+
+def tree_nodes_from_desc(desc):
+    """dc_fk_desc.tree -> the node list oracle.fk_joint_tree takes."""
+    kinds = {0: "fixed", 1: "x", 2: "y", 3: "z", 4: "prismatic"}
+    nodes = []
+    for i in range(desc.n_nodes):
+        nd = desc.tree[i]
+        nodes.append({"parent": nd.parent, "q_index": nd.q_index, "joint": kinds[nd.joint], "sign": nd.axis[0],
+                      "axis": torch.tensor(list(nd.axis), dtype=torch.float64), "out_slot": nd.out_slot,
+                      "rot": torch.tensor(list(nd.rot), dtype=torch.float64).reshape(3, 3),
+                      "trans": torch.tensor(list(nd.trans), dtype=torch.float64), "mimic_mul": nd.mimic_mul,
+                      "mimic_off": nd.mimic_off})
+    return nodes

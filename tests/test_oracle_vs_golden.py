@@ -330,3 +330,36 @@ def test_line_and_temporal_kernels_match_reference():
     close(xv.grad, g["l_grad"], 1e-11)
     close(O.line_fk_kernel(xl[0], sl, fk, 10.0), g["l_K_single"])
     close(O.line_kernel(xl, sl, lambda a, b: O.rq_kernel(a, b, 2.0)), g["lk_K"])
+
+
+@pytest.mark.parametrize("name", ["arm7", "torso", "panda"])
+def test_urdf_tree_fk_matches_reference(name):
+    """rigid_body.py:86-141 through urdf_interface.py:517-553 (float32 in the reference): the float64 restatement run on the
+    joint program this package compiled — for arm7 / torso compiled HERE from tests/data/*.urdf (so the XML parser and the
+    compiler are pinned too; the golden's tree was built by an independent parse in oracle/make_golden.py), for the Panda
+    from the descriptor bytes stored in the golden (the reference's file does not travel)."""
+    from diffco_b200 import _lib
+    from diffco_b200.collision_interfaces import URDFRobot
+
+    g = load("urdf.npz")
+    stored = _lib.FkDesc.from_buffer_copy(g[name + "_desc"].tobytes())
+    if name != "panda":
+        base = None if name == "arm7" else torch.tensor([[0.0, -1.0, 0.0, 0.3], [1.0, 0.0, 0.0, -0.2], [0.0, 0.0, 1.0, 0.1],
+                                                          [0, 0, 0, 1.0]])
+        path = os.path.join(os.path.dirname(__file__), "data", {"arm7": "arm7_gripper.urdf", "torso": "torso_two_arms.urdf"}[name])
+        robot = URDFRobot(path, base_transform=base)
+        assert bytes(robot.fk_desc) == bytes(stored)
+        assert robot.unique_position_link_names == list(g[name + "_unique"]) and robot.node_names == list(g[name + "_nodes"])
+        close(robot.joint_limits, g[name + "_limits"], 1e-7)
+        desc = robot.fk_desc
+    else:
+        desc = stored
+    nodes = P.tree_nodes_from_desc(desc)
+    q = T64(g[name + "_q"]).requires_grad_(True)
+    x, frames = O.fk_joint_tree(q, nodes, desc.n_points)
+    close(x.detach().transpose(1, 2), g[name + "_x"], 3e-6)  # reference layout (B, 3, L), float32 arithmetic
+    (x.transpose(1, 2) * T64(g[name + "_gx"])).sum().backward()
+    close(q.grad, g[name + "_gq"], 1e-5)
+    order = [list(g[name + "_nodes"]).index(k) for k in g[name + "_links"]]
+    close(torch.stack([frames[i][1] for i in order], 1).detach(), g[name + "_trans"], 3e-6)
+    close(torch.stack([frames[i][0] for i in order], 1).detach(), g[name + "_rot"], 3e-6)
