@@ -409,27 +409,34 @@ __device__ __noinline__ void fk_forward(const dc_fk_desc& fk, const T* q, T* xp,
 // sin / cos in float64 to ~1e-13 absolute — all the (hi, lo) float32 feature pairs need (lo is ~1e-7 of hi) — at a
 // fifth of the instruction count of libm's sincos: two-term Cody-Waite reduction to [-pi/4, pi/4], Taylor polynomials
 // (sin to x^15, cos to x^14: truncation < 5e-13 at pi/4).  Arguments here are sums of joint angles (|x| < a few hundred).
+// Polynomial coefficients live in constant memory: a DFMA takes them as c[bank][offset] operands, whereas literals are
+// materialised as two 32-bit moves each — a fifth of the instructions of the unrolled planar chain.
+static __constant__ double kSinCos64[19] = {
+    0.63661977236758134308, 1.57079632673412561417, 6.07710050650619224932e-11,
+    1.0 / 1307674368000.0, -1.0 / 6227020800.0, 1.0 / 39916800.0, -1.0 / 362880.0, 1.0 / 5040.0, -1.0 / 120.0, 1.0 / 6.0,
+    -1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5, 1.0, 0.0};
 __device__ __forceinline__ void sincos_fast64(double x, double* s, double* c) {
-  const double kd = rint(x * 0.63661977236758134308);        // x / (pi/2)
-  double r = fma(-kd, 1.57079632673412561417, x);            // pi/2 = P1 + P2, P1 exact in 33 bits
-  r = fma(-kd, 6.07710050650619224932e-11, r);
+  const double* K = kSinCos64;
+  const double kd = rint(x * K[0]);          // x / (pi/2)
+  double r = fma(-kd, K[1], x);              // pi/2 = P1 + P2, P1 exact in 33 bits
+  r = fma(-kd, K[2], r);
   const double r2 = r * r;
-  double sp = 1.0 / 1307674368000.0;                         // 1/15!
-  sp = fma(sp, r2, -1.0 / 6227020800.0);
-  sp = fma(sp, r2, 1.0 / 39916800.0);
-  sp = fma(sp, r2, -1.0 / 362880.0);
-  sp = fma(sp, r2, 1.0 / 5040.0);
-  sp = fma(sp, r2, -1.0 / 120.0);
-  sp = fma(sp, r2, 1.0 / 6.0);
-  sp = fma(-sp * r2, r, r);                                  // r - r^3 (1/6 - ...)
-  double cp = -1.0 / 87178291200.0;                          // -1/14!
-  cp = fma(cp, r2, 1.0 / 479001600.0);
-  cp = fma(cp, r2, -1.0 / 3628800.0);
-  cp = fma(cp, r2, 1.0 / 40320.0);
-  cp = fma(cp, r2, -1.0 / 720.0);
-  cp = fma(cp, r2, 1.0 / 24.0);
-  cp = fma(cp, r2, -0.5);
-  cp = fma(cp, r2, 1.0);
+  double sp = K[3];                          // 1/15!
+  sp = fma(sp, r2, K[4]);
+  sp = fma(sp, r2, K[5]);
+  sp = fma(sp, r2, K[6]);
+  sp = fma(sp, r2, K[7]);
+  sp = fma(sp, r2, K[8]);
+  sp = fma(sp, r2, K[9]);
+  sp = fma(-sp * r2, r, r);                  // r - r^3 (1/6 - ...)
+  double cp = K[10];                         // -1/14!
+  cp = fma(cp, r2, K[11]);
+  cp = fma(cp, r2, K[12]);
+  cp = fma(cp, r2, K[13]);
+  cp = fma(cp, r2, K[14]);
+  cp = fma(cp, r2, K[15]);
+  cp = fma(cp, r2, K[16]);
+  cp = fma(cp, r2, K[17]);
   const int k = (int)kd;
   const double s0 = (k & 1) ? cp : sp, c0 = (k & 1) ? sp : cp;
   *s = (k & 2) ? -s0 : s0;

@@ -47,6 +47,9 @@
 #define DC_TC_PREFETCH 0  // 1: the first two tcgen05.ld of chunk g + 1 are issued at the end of chunk g (before its st-wait /
 #endif                    //    arrive / loop top): 99.8 us vs 95.2 us — the two buffers stay live across the loop edge and
                           //    ptxas spills (112 bytes) what it saves in latency (profiles/r02q_variants.txt)
+#ifndef DC_TC_FK_UNROLL
+#define DC_TC_FK_UNROLL 1  // joints per iteration of the planar FK loop of the tile prologue (code size vs. latency overlap)
+#endif
 #ifndef DC_TC_DEPHASE
 #define DC_TC_DEPHASE 0   // 1: the owner half starts each tile half a chunk behind the lower half: 93.6 us vs 92.9 us
 #endif
@@ -89,6 +92,9 @@ struct TcLayout {
   static constexpr int QS_DOF = 8;   // staged configurations: dof <= 8 for real feature maps (FK NONE needs none)
   // shared memory (bytes)
   static constexpr int SM_BAR = 0;
+  static constexpr int SM_TRAILER = 136;    // the blob's trailer floats 0..11, copied once per CTA (bytes 136 .. 184)
+  static constexpr int SM_TILE0 = 184;      // first tile of this CTA (long long): the out-of-line stages read it back
+                                            // instead of redoing the 64-bit division (cold code on the tile-to-tile path)
   static constexpr int SM_TMEM_SLOT = 192;
   static constexpr int SM_RING1 = 256;
   static constexpr int SM_RING2 = SM_RING1 + RS1 * B1_BYTES;
@@ -226,19 +232,32 @@ __device__ __forceinline__ bool mbar_test(uint32_t addr, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// The waiting thread is suspended by the hardware until the phase completes or the time hint (ns) expires, so a waiting
+// warp issues a handful of instructions per microsecond instead of spinning: with the default (short, system-dependent)
+// time limit the four service warps' spin loops were 23 % of all instructions the kernel issued and competed with the
+// query warps for issue slots (profiles/r02y_score_tc_bench_hot_sass.txt: 1.75 M loop iterations x 8 instructions per launch).
+#ifndef DC_TC_WAIT_HINT_NS
+#define DC_TC_WAIT_HINT_NS 20000
+#endif
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   if (mbar_test(addr, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
+  long long t0 = 0;
   for (;;) {
     uint32_t done;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"((uint32_t)DC_TC_WAIT_HINT_NS)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 60000000000LL) __trap();  // ~30 s: a protocol bug, not a slow launch
+    if ((++spins & 1023u) == 0) {  // watchdog, off the fast path: ~30 s means a protocol bug, not a slow launch
+      if (t0 == 0)
+        t0 = clock64();
+      else if (clock64() - t0 > 60000000000LL)
+        __trap();
+    }
   }
 }
 
@@ -524,11 +543,12 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
   __half* xlo_all = reinterpret_cast<__half*>(smem + L::SM_XLO);
   float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);
   float2* thr_all = reinterpret_cast<float2*>(smem + L::SM_ROWS + TM * 4);
-  const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
+  const long long t0 = *reinterpret_cast<const long long*>(smem + L::SM_TILE0);
 #ifdef DC_TC_ENABLE_TRACE
   const int nch = a.n_chunks;
 #endif
-  const float* trailer = tc_trailer(a.blob, a.n_sv);
+  DC_TC_TRACE_TILE(0, 7);
+  const float* trailer = reinterpret_cast<const float*>(smem + L::SM_TRAILER);
   const float sa = trailer[3], tc0 = trailer[4];
   const int F = a.n_feat;
   const bool has_fk = a.fk.type != DC_FK_NONE;
@@ -539,106 +559,161 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
   float* qs = qs_all + buf * TM * L::QS_DOF;
   const float* src = a.q + (size_t)b_base * a.n_in;
   const int n_words = nq * a.n_in;
-  float x[FM], xlo[FM];  // features as float32 (hi, lo) pairs of a float64 evaluation (dc_fk.cuh: fk_forward_f32x)
-  float qv[DC_MAX_DOF];
-  if (has_fk) {
-    // the tile's configurations were staged (coalesced) by the prefetch warp while the previous tile was being scored
+  float xx = 0.f, xamax = 0.f;
+  bool in_range;
+  const float xlo_sc = (float)(1 << L::XLO_SCALE_LOG2);
+  if (has_fk && a.fk.type == DC_FK_PLANAR_CHAIN && a.fk.n_repeat <= 1 && !a.fk.time_last) {
+    // The BASELINE robot.  One ROLLED loop over the joints that writes features, low parts and the A-operand words
+    // straight to shared memory: this stage runs once per tile on four warps, its code is cold every time, and as
+    // 1150 unrolled instructions it spent half its cycles waiting for instruction fetches (ncu: stall_no_inst, 53 % of
+    // the stage's samples).  The arithmetic per joint is fk_planar_f64_reg's, operation for operation, so the features
+    // are bit-identical to dc_fk_forward's (support_transformed) and to every other kernel's.
     mbar_wait_wd(bar_qfull + buf, (uint32_t)((ti >> 1) & 1));
+    DC_TC_TRACE_TILE(0, 4);
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (row < nq && i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
-    if (a.fk.type == DC_FK_PLANAR_CHAIN) {
-      // the BASELINE robot: the chain in registers, float64 with the short sincos (== fk_forward_f32x's planar branch)
-      double xd[16];
-      fk_planar_f64_reg<8>(a.fk.link_length, a.fk.n_links, qv, xd);
+    for (int kc = 0; kc < L::K1 / 8; ++kc) reinterpret_cast<uint4*>(a_op)[kc * TM + row] = z4;
+    {
+      uint4* xr = reinterpret_cast<uint4*>(xs + row * 16);
+      xr[0] = z4, xr[1] = z4, xr[2] = z4, xr[3] = z4;
+      uint4* lr = reinterpret_cast<uint4*>(xlo_all + (buf * TM + row) * 16);
+      lr[0] = z4, lr[1] = z4;
+    }
+    const int nl = (row < nq) ? a.fk.n_links : 0;
+    const float* qr = qs + row * a.n_in;
+    unsigned char* arow = a_op + row * 16;
+    double th = 0.0, px = 0.0, py = 0.0;
+    constexpr int kFkUnroll = DC_TC_FK_UNROLL;
+#pragma unroll kFkUnroll
+    for (int i = 0; i < nl; ++i) {
+      th += (double)qr[i];
+      double sn, cs;
+      sincos_fast64(th, &sn, &cs);
+      const double len = a.fk.link_length[i];
+      px = fma(len, cs, px);
+      py = fma(len, sn, py);
+      const float hx = (float)px, hy = (float)py;
+      const float lx = (float)(px - (double)hx), ly = (float)(py - (double)hy);
+      *reinterpret_cast<float2*>(xs + row * 16 + 2 * i) = make_float2(hx, hy);
+      reinterpret_cast<uint32_t*>(xlo_all + (buf * TM + row) * 16)[i] = pack_f16x2(lx * xlo_sc, ly * xlo_sc);
+      xx = fmaf(hx, hx, xx);
+      xx = fmaf(hy, hy, xx);
+      xamax = fmaxf(xamax, fmaxf(fabsf(hx), fabsf(hy)));
+      // K slots 2i, 2i + 1 (x beta s_h), 16 + .. (x beta s_h / 256), 32 + .. (x 256 (beta s)_lo)
+      const float ax = sa * hx, ay = sa * hy;
+      const float hix = split_hi(ax), hiy = split_hi(ay);
+      unsigned char* aw = arow + ((2 * i) >> 3) * (TM * 16) + ((2 * i) & 7) * 2;
+      *reinterpret_cast<uint32_t*>(aw) = pack_f16x2(hix, hiy);
+      *reinterpret_cast<uint32_t*>(aw + 2 * (TM * 16)) = pack_f16x2((ax - hix) * 256.f, (ay - hiy) * 256.f);
+      *reinterpret_cast<uint32_t*>(aw + 4 * (TM * 16)) = pack_f16x2(hix * (1.f / 256.f), hiy * (1.f / 256.f));
+    }
+    DC_TC_TRACE_TILE(0, 5);
+    // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
+    in_range = (sa * xamax < 32768.f) && (tc0 * xx < 32768.f);
+    if (!in_range) {
 #pragma unroll
-      for (int f = 0; f < FM; ++f) {
-        x[f] = (float)xd[f];
-        xlo[f] = (float)(xd[f] - (double)x[f]);
+      for (int kc = 0; kc < L::K1 / 8; ++kc) reinterpret_cast<uint4*>(a_op)[kc * TM + row] = z4;
+    }
+    const float XX = in_range ? tc0 * xx : 0.f;
+    const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
+    *reinterpret_cast<uint32_t*>(arow + 1 * (TM * 16) + 12) = pack_f16x2(1.f, 1.f);  // slots 14, 15: x S1, x S2
+    *reinterpret_cast<uint32_t*>(arow + 3 * (TM * 16) + 12) = pack_f16x2(1.f, x1);   // slots 30, 31: x S3, x 1
+    *reinterpret_cast<uint32_t*>(arow + 5 * (TM * 16) + 12) = pack_f16x2(x2, x3);    // slots 46, 47: x 1, x 1
+  } else {
+    float x[FM], xlo[FM];  // features as float32 (hi, lo) pairs of a float64 evaluation (dc_fk.cuh: fk_forward_f32x)
+    float qv[DC_MAX_DOF];
+    if (has_fk) {
+      // the tile's configurations were staged (coalesced) by the prefetch warp while the previous tile was being scored
+      mbar_wait_wd(bar_qfull + buf, (uint32_t)((ti >> 1) & 1));
+      DC_TC_TRACE_TILE(0, 4);
+#pragma unroll
+      for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (row < nq && i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
+      {
+        float xh16[DC_MAX_DOF], xl16[DC_MAX_DOF];
+#pragma unroll
+        for (int i = 0; i < DC_MAX_DOF; ++i) xh16[i] = xl16[i] = 0.f;
+        if (row < nq) fk_forward_f32x<true>(a.fk, qv, xh16, 1, xl16, 1);
+#pragma unroll
+        for (int f = 0; f < FM; ++f) {
+          x[f] = (f < F) ? xh16[f] : 0.f;
+          xlo[f] = (f < F) ? xl16[f] : 0.f;
+        }
       }
     } else {
-      float xh16[DC_MAX_DOF], xl16[DC_MAX_DOF];
-#pragma unroll
-      for (int i = 0; i < DC_MAX_DOF; ++i) xh16[i] = xl16[i] = 0.f;
-      if (row < nq) fk_forward_f32x<true>(a.fk, qv, xh16, 1, xl16, 1);
+      // transform=None: the rows ARE the features; staged straight into the feature layout [128][16]
+      for (int i = tid; i < TM * 16; i += TM) xs[i] = 0.f;
+      named_sync(TCB_LOW, TM);
+      for (int i = tid; i < n_words; i += TM) {
+        const int r = i / a.n_in;
+        xs[r * 16 + (i - r * a.n_in)] = src[i];
+      }
+      named_sync(TCB_LOW, TM);
 #pragma unroll
       for (int f = 0; f < FM; ++f) {
-        x[f] = (f < F) ? xh16[f] : 0.f;
-        xlo[f] = (f < F) ? xl16[f] : 0.f;
+        x[f] = xs[row * 16 + f];
+        xlo[f] = 0.f;
       }
     }
-  } else {
-    // transform=None: the rows ARE the features; staged straight into the feature layout [128][16]
-    for (int i = tid; i < TM * 16; i += TM) xs[i] = 0.f;
-    named_sync(TCB_LOW, TM);
-    for (int i = tid; i < n_words; i += TM) {
-      const int r = i / a.n_in;
-      xs[r * 16 + (i - r * a.n_in)] = src[i];
+    DC_TC_TRACE_TILE(0, 5);
+    {
+      const float sc = (float)(1 << L::XLO_SCALE_LOG2);
+      uint4* lr = reinterpret_cast<uint4*>(xlo_all + (buf * TM + row) * 16);
+      uint4 l0, l1;
+      l0.x = pack_f16x2(xlo[0] * sc, xlo[1] * sc), l0.y = pack_f16x2(xlo[2] * sc, xlo[3] * sc);
+      l0.z = pack_f16x2(xlo[4] * sc, xlo[5] * sc), l0.w = pack_f16x2(xlo[6] * sc, xlo[7] * sc);
+      l1.x = pack_f16x2(xlo[8] * sc, xlo[9] * sc), l1.y = pack_f16x2(xlo[10] * sc, xlo[11] * sc);
+      l1.z = pack_f16x2(xlo[12] * sc, xlo[13] * sc), l1.w = 0u;
+      lr[0] = l0;
+      lr[1] = l1;
     }
-    named_sync(TCB_LOW, TM);
 #pragma unroll
     for (int f = 0; f < FM; ++f) {
-      x[f] = xs[row * 16 + f];
-      xlo[f] = 0.f;
+      xx = fmaf(x[f], x[f], xx);
+      xamax = fmaxf(xamax, fabsf(x[f]));
     }
-  }
-  {
-    const float sc = (float)(1 << L::XLO_SCALE_LOG2);
-    uint4* lr = reinterpret_cast<uint4*>(xlo_all + (buf * TM + row) * 16);
-    uint4 l0, l1;
-    l0.x = pack_f16x2(xlo[0] * sc, xlo[1] * sc), l0.y = pack_f16x2(xlo[2] * sc, xlo[3] * sc);
-    l0.z = pack_f16x2(xlo[4] * sc, xlo[5] * sc), l0.w = pack_f16x2(xlo[6] * sc, xlo[7] * sc);
-    l1.x = pack_f16x2(xlo[8] * sc, xlo[9] * sc), l1.y = pack_f16x2(xlo[10] * sc, xlo[11] * sc);
-    l1.z = pack_f16x2(xlo[12] * sc, xlo[13] * sc), l1.w = 0u;
-    lr[0] = l0;
-    lr[1] = l1;
-  }
-  float xx = 0.f, xamax = 0.f;
-#pragma unroll
-  for (int f = 0; f < FM; ++f) {
-    xx = fmaf(x[f], x[f], xx);
-    xamax = fmaxf(xamax, fabsf(x[f]));
-  }
-  {
-    float4* xr = reinterpret_cast<float4*>(xs + row * 16);
-    xr[0] = make_float4(x[0], x[1], x[2], x[3]);
-    xr[1] = make_float4(x[4], x[5], x[6], x[7]);
-    xr[2] = make_float4(x[8], x[9], x[10], x[11]);
-    xr[3] = make_float4(x[12], x[13], 0.f, 0.f);
-  }
-  // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
-  const bool in_range = (sa * xamax < 32768.f) && (tc0 * xx < 32768.f);
-  {
-    float v[L::K1];
-    const float XX = in_range ? tc0 * xx : 0.f;
-#pragma unroll
-    for (int k = 0; k < L::K1; ++k) v[k] = 0.f;
-#pragma unroll
-    for (int f = 0; f < FM; ++f) {
-      const float xsc = in_range ? sa * x[f] : 0.f;
-      const float hi = split_hi(xsc);
-      v[f] = hi;                       // x beta s_h
-      v[16 + f] = (xsc - hi) * 256.f;  // x beta s_h / 256
-      v[32 + f] = hi * (1.f / 256.f);  // x 256 (beta s)_lo
+    {
+      float4* xr = reinterpret_cast<float4*>(xs + row * 16);
+      xr[0] = make_float4(x[0], x[1], x[2], x[3]);
+      xr[1] = make_float4(x[4], x[5], x[6], x[7]);
+      xr[2] = make_float4(x[8], x[9], x[10], x[11]);
+      xr[3] = make_float4(x[12], x[13], 0.f, 0.f);
     }
-    const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
-    v[14] = 1.f;  // x S1   (S = tau (1 + c0 |s|^2), three terms)
-    v[15] = 1.f;  // x S2
-    v[30] = 1.f;  // x S3
-    v[31] = x1;   // x 1
-    v[46] = x2;   // x 1
-    v[47] = x3;   // x 1
+    // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
+    in_range = (sa * xamax < 32768.f) && (tc0 * xx < 32768.f);
+    {
+      float v[L::K1];
+      const float XX = in_range ? tc0 * xx : 0.f;
 #pragma unroll
-    for (int kc = 0; kc < L::K1 / 8; ++kc) {
-      uint4 pk;
-      pk.x = pack_f16x2(v[8 * kc + 0], v[8 * kc + 1]);
-      pk.y = pack_f16x2(v[8 * kc + 2], v[8 * kc + 3]);
-      pk.z = pack_f16x2(v[8 * kc + 4], v[8 * kc + 5]);
-      pk.w = pack_f16x2(v[8 * kc + 6], v[8 * kc + 7]);
-      reinterpret_cast<uint4*>(a_op)[kc * TM + row] = pk;
+      for (int k = 0; k < L::K1; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int f = 0; f < FM; ++f) {
+        const float xsc = in_range ? sa * x[f] : 0.f;
+        const float hi = split_hi(xsc);
+        v[f] = hi;                       // x beta s_h
+        v[16 + f] = (xsc - hi) * 256.f;  // x beta s_h / 256
+        v[32 + f] = hi * (1.f / 256.f);  // x 256 (beta s)_lo
+      }
+      const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
+      v[14] = 1.f;  // x S1   (S = tau (1 + c0 |s|^2), three terms)
+      v[15] = 1.f;  // x S2
+      v[30] = 1.f;  // x S3
+      v[31] = x1;   // x 1
+      v[46] = x2;   // x 1
+      v[47] = x3;   // x 1
+#pragma unroll
+      for (int kc = 0; kc < L::K1 / 8; ++kc) {
+        uint4 pk;
+        pk.x = pack_f16x2(v[8 * kc + 0], v[8 * kc + 1]);
+        pk.y = pack_f16x2(v[8 * kc + 2], v[8 * kc + 3]);
+        pk.z = pack_f16x2(v[8 * kc + 4], v[8 * kc + 5]);
+        pk.w = pack_f16x2(v[8 * kc + 6], v[8 * kc + 7]);
+        reinterpret_cast<uint4*>(a_op)[kc * TM + row] = pk;
+      }
     }
   }
   fence_proxy_async();
   mbar_arrive(bar_a);
+  DC_TC_TRACE_TILE(0, 6);
   {
     // near threshold of this query on T as a line in the chunk's max|s|^2: pairs with 1 + c0 rho < (gamma drho / tol)^(1/3),
     // drho = err (|x|^2 + max_chunk |s|^2), are recomputed exactly.  The cube root is bounded from above by its tangent at the
@@ -646,7 +721,7 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
     const float s2max = trailer[0], tau = trailer[5];
     const float kq = -a.rc.grad_scale * 0.5f * a.err_coef / a.tol_pair;  // gamma err / tol
     const float base = fmaxf(kq * (xx + s2max), 1.f);
-    const float cr = cbrtf(base);
+    const float cr = exp2f(__log2f(base) * (1.f / 3.f));  // two MUFU ops; the 0.1 % margin below covers their error
     const float c1 = tau * 1.001f * kq / (3.f * cr * cr);
     const float c0 = in_range ? tau * 1.001f * cr - c1 * s2max : 3.0e38f;  // out-of-range rows: every pair is "near"
     thr_all[buf * TM + row] = make_float2(c0, c1);
@@ -654,7 +729,7 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
 #ifdef DC_TC_ENABLE_TRACE
   if (a.dbg != nullptr && t0 + ti == 0) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) a.dbg[(size_t)TM * (nch * NC) + TM * 32 + row * 16 + c] = c < FM ? x[c] : 0.f;
+    for (int c = 0; c < 16; ++c) a.dbg[(size_t)TM * (nch * NC) + TM * 32 + row * 16 + c] = c < FM ? xs[row * 16 + c] : 0.f;
   }
 #endif
   named_arrive(TCB_FK, QT);  // features, |x|^2 (and the staged configurations) of tile ti are visible to the owners
@@ -683,7 +758,7 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
   float* gacc_w = gacc + warp * 32 * 16;
   float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);
   const float* sc_p = reinterpret_cast<const float*>(smem + L::SM_ROWS);
-  const long long t0 = (long long)blockIdx.x * a.n_tiles / gridDim.x;
+  const long long t0 = *reinterpret_cast<const long long*>(smem + L::SM_TILE0);
   const long long b_base = (t0 + ti) * TM;
   const int nq = (int)min((long long)TM, a.batch - b_base);
   const int F = a.n_feat;
@@ -691,7 +766,7 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
   const bool fused = (MODE == TC_GRAD) ? (a.score_ld == a.grad_ld && a.score_ld == n_out && a.grad == a.score + 1)
                                        : (a.score_ld == 1);
   const bool has_fk = a.fk.type != DC_FK_NONE;
-  const float inv_g = tc_trailer(a.blob, a.n_sv)[6];
+  const float inv_g = reinterpret_cast<const float*>(smem + L::SM_TRAILER)[6];
 #ifdef DC_TC_ENABLE_TRACE
   const int nch = a.n_chunks;
 #endif
@@ -878,6 +953,10 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
     }
     __syncwarp();
     tmem_alloc(tmem_slot, L::TMEM_COLS);
+  } else if (warp == 0 && lane < 12) {
+    reinterpret_cast<float*>(smem + L::SM_TRAILER)[lane] = tc_trailer(a.blob, a.n_sv)[lane];
+  } else if (warp == 1 && lane == 0) {
+    *reinterpret_cast<long long*>(smem + L::SM_TILE0) = t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -1174,7 +1253,8 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
 
       if (!owner) {
         sc_p[row] = sc2.lo() + sc2.hi();
-        __threadfence_block();
+        // bar.arrive orders this thread's prior shared-memory writes for the threads that complete the barrier; a
+        // sequentially consistent fence here (MEMBAR.SC) cost ~2000 cycles per tile on the path to the next tile's FK
         named_arrive(TCB_EPI, QT);  // lower half's partial scores and exact terms of tile ti are complete
         if (ti + 1 < ntile) tc_fk_stage(a, ti + 1, tid);
         DC_TC_TRACE_TILE(0, 3);

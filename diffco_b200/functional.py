@@ -237,45 +237,68 @@ def fk_tree_frames(fk: FkDesc, q: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------------
 
 
-class _ScoreFunction(torch.autograd.Function):
-    """score = evaluator(q) with the analytic Jacobian stashed for backward.
+def _is_batched(t) -> bool:
+    """True inside a vmapped backward (``jacobian(vectorize=True)``, ``is_grads_batched``): such tensors have no storage a
+    CUDA launch could read."""
+    try:
+        return bool(torch._C._functorch.is_batchedtensor(t))
+    except Exception:
+        return False
 
-    ``evaluator(q_dev, want_jac) -> (score (B,C), jac (B,C,D) | None)`` runs the fused CUDA kernel.  backward is
-    a multiply + sum over classes — pure torch ops on the stashed Jacobian — so it also works when autograd batches the
-    upstream gradient (``torch.autograd.functional.jacobian(vectorize=True)``, diffco/optim.py:211-216).  The
-    Jacobian is a constant w.r.t. autograd: second derivatives (optim.py:380-391, trust-constr Hessians) are not
-    provided and fail loudly instead of silently returning zeros.
+
+class _ScoreFunction(torch.autograd.Function):
+    """score = evaluator(q) with an analytic backward.
+
+    ``evaluator(q, mode, grad_out) -> (score (B, C), grad)`` runs the fused CUDA kernel (modes of ``dc_score_grad``).
+
+    * One class: forward is ONE launch that also returns the Jacobian ``(B, 1, D)``; backward is a multiply.
+    * Several classes: forward returns the scores only.  backward launches the kernel once more with the upstream gradient
+      (``DC_GRAD_SUM``: ``(B, D)`` out) — not the ``(B, C, D)`` Jacobian, C times the output the optimisers need
+      (diffco/optim.py:101,734 differentiate a sum).  Only when autograd batches the upstream gradient
+      (``torch.autograd.functional.jacobian(vectorize=True)``, diffco/optim.py:211-216) is the full Jacobian evaluated —
+      on the unbatched ``q`` — and contracted with pure torch ops (mul + sum have batching rules, a CUDA launch does not).
+
+    The gradient is a constant w.r.t. autograd: second derivatives (optim.py:380-391) are not provided through autograd
+    (``optim.trustconstr_traj_optimize`` takes finite differences of this first derivative) and fail loudly instead of
+    silently returning zeros.
     """
 
     @staticmethod
     def forward(q, evaluator):
-        score, jac = evaluator(q, q.requires_grad or torch.is_grad_enabled())
-        return score, jac
+        want = q.requires_grad or torch.is_grad_enabled()
+        if want and getattr(evaluator, "n_class", 1) == 1:
+            return evaluator(q, _lib.DC_GRAD_JAC)
+        score, _ = evaluator(q, _lib.DC_GRAD_NONE)
+        return score, None
 
     @staticmethod
     def setup_context(ctx, inputs, output):
+        q, evaluator = inputs
         _, jac = output
-        ctx.save_for_backward(jac)
-        ctx.mark_non_differentiable(jac)
+        ctx.evaluator = evaluator
+        if jac is not None:
+            ctx.save_for_backward(jac)
+            ctx.mark_non_differentiable(jac)
+        else:
+            ctx.save_for_backward(q)
+        ctx.has_jac = jac is not None
         ctx.set_materialize_grads(False)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_score, _grad_jac):
-        (jac,) = ctx.saved_tensors
         if grad_score is None:
             return None, None
+        if ctx.has_jac:
+            (jac,) = ctx.saved_tensors
+        else:
+            (q,) = ctx.saved_tensors
+            if not _is_batched(grad_score):
+                _, grad = ctx.evaluator(q, _lib.DC_GRAD_SUM, grad_score)
+                return grad.to(q.dtype), None
+            _, jac = ctx.evaluator(q, _lib.DC_GRAD_JAC)
         # mul + sum (not einsum / bmm): both have batching rules, which the vmapped backward needs
         return (grad_score.to(jac.dtype).unsqueeze(-1) * jac).sum(-2), None
-
-
-def differentiable_score(q: torch.Tensor, evaluator) -> torch.Tensor:
-    """Run ``evaluator`` on q (any device / dtype handled by the evaluator) with autograd support."""
-    if q.requires_grad and torch.is_grad_enabled():
-        score, _ = _ScoreFunction.apply(q, evaluator)
-        return score
-    score, _ = evaluator(q, False)
-    return score
 
 
 class _FkFunction(torch.autograd.Function):

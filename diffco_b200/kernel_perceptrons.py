@@ -85,14 +85,19 @@ class _FusedScorer:
         return self._fk_desc if self._fk_desc is not None else functional.none_fk(sv.n_features)
 
     def _evaluator(self, sv, kdesc, fk):
-        def run(q_in, want_jac):
+        def run(q_in, mode, grad_out=None):
+            """mode DC_GRAD_NONE -> (score, None); DC_GRAD_JAC -> (score, (B, C, D)); DC_GRAD_SUM -> (score, (B, D)) =
+            d(sum_c grad_out[:, c] score[:, c])/dq."""
             q = q_in.detach().to(device=sv.device, dtype=sv.dtype)
-            score, jac = functional.score_grad(fk, kdesc, sv, q, DC_GRAD_JAC if want_jac else DC_GRAD_NONE)
+            if grad_out is not None:
+                grad_out = grad_out.detach().to(device=sv.device, dtype=sv.dtype)
+            score, grad = functional.score_grad(fk, kdesc, sv, q, mode, grad_out)
             score = score.to(q_in.device)
-            if jac is not None:
-                jac = jac.to(device=q_in.device, dtype=q_in.dtype)
-            return score, jac
+            if grad is not None:
+                grad = grad.to(device=q_in.device, dtype=q_in.dtype)
+            return score, grad
 
+        run.n_class = sv.n_class
         return run
 
     def _fused(self, point, sv, kernel_func, fk):

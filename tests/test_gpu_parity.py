@@ -427,6 +427,54 @@ def test_legacy_multiclass_matches_reference(dev):
     assert rel(jac.permute(1, 0, 2), g["rbf_jac"]) <= 1e-8
 
 
+def test_multiclass_backward_launches_the_sum_mode_not_the_jacobian(dev, monkeypatch):
+    """Several classes: forward = scores only; backward = one more launch in DC_GRAD_SUM with the upstream gradient
+    ((B, D) out) instead of the (B, C, D) Jacobian; only a vmapped backward (jacobian(vectorize=True), optim.py:211-216)
+    evaluates the full Jacobian.  One class keeps the single launch that returns the Jacobian with the scores."""
+    from diffco_b200 import DiffCo, MultiDiffCo, _lib
+    from diffco_b200 import functional as Fn
+    from diffco_b200 import kernel as K
+
+    robot, S, W = P.synthetic_model("baxter", 300, 4, seed=3)
+    mdc = MultiDiffCo(None, kernel_func=K.FKKernel(robot.fkine, K.RQKernel(10.0)), beta=1.0)
+    mdc.support_points = S.to(dev)
+    mdc.support_transformed = robot.fkine(mdc.support_points)
+    mdc.gains = W.to(dev)
+    modes, orig = [], Fn.score_grad
+
+    def spy(fk, kernel, sv, q, grad_mode=_lib.DC_GRAD_NONE, grad_out=None, out=None):
+        modes.append(grad_mode)
+        return orig(fk, kernel, sv, q, grad_mode, grad_out, out)
+
+    monkeypatch.setattr(Fn, "score_grad", spy)
+    Q = P.sample_configs(robot, 50, torch.Generator().manual_seed(4))
+    go = torch.randn(50, 4, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    qv = Q.clone().requires_grad_(True)
+    (mdc.score(qv) * go).sum().backward()
+    assert modes == [_lib.DC_GRAD_NONE, _lib.DC_GRAD_SUM]
+    _, want = mdc.score_and_grad(Q.to(dev), grad_out=go.to(dev))
+    assert rel(qv.grad, want.cpu().numpy()) <= 1e-13
+    modes.clear()
+    jac = torch.autograd.functional.jacobian(lambda q: mdc.score(q).sum(0), Q, vectorize=True)  # (C, B, D)
+    assert modes == [_lib.DC_GRAD_NONE, _lib.DC_GRAD_JAC]
+    for c in range(4):
+        e = torch.zeros(50, 4, dtype=torch.float64)
+        e[:, c] = 1
+        _, gc = orig(mdc._fk_for(mdc._select("gains")[0]), mdc._select("gains")[1].desc, mdc._select("gains")[0], Q.to(dev),
+                     _lib.DC_GRAD_SUM, e.to(dev))
+        assert rel(jac[c], gc.cpu().numpy()) <= 1e-13
+    # one class: a single launch
+    robot1, S1, W1 = P.synthetic_model("planar7", 200, 1, seed=6)
+    dc = DiffCo(kernel_func=K.RQKernel(10.0), transform=robot1.fkine)
+    dc.support_points = S1.to(dev)
+    dc.support_transformed = robot1.fkine(dc.support_points)
+    dc.gains = W1[:, 0].to(dev)
+    modes.clear()
+    q1 = P.sample_configs(robot1, 30, torch.Generator().manual_seed(7)).requires_grad_(True)
+    dc.score(q1).sum().backward()
+    assert modes == [_lib.DC_GRAD_JAC]
+
+
 def test_optimizer_call_pattern_replay(dev):
     """The queries the reference's adam_/givengrad_traj_optimize issued (recorded by oracle/make_golden.py), replayed
     through the CUDA dist_est with the exact autograd usage of optim.py:86-103 and :190-218."""

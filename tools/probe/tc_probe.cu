@@ -160,6 +160,8 @@ int main(int argc, char** argv) {
     }
     printf("tile events (cycles rel. to chunk-0 start of tile 0): lower half: loop start, loop end, drained, next FK done | owners: loop start, loop end, drained, G ready, records, stored\n");
     for (int ti = 0; ti < 3; ++ti) { printf("tile %d:", ti); for (int ev : {0, 1, 2, 3, 8, 9, 10, 11, 12, 13}) printf(" %7lld", tr[(50 + ev) * 16 + ti] ? tr[(50 + ev) * 16 + ti] - b0 : -1); printf("\n"); }
+    printf("FK stage of each tile (lower half, warp 0): entered, configurations staged, float64 FK done, A operand published\n");
+    for (int ti = 0; ti < 3; ++ti) { printf("tile %d:", ti); for (int ev : {7, 4, 5, 6}) printf(" %7lld", tr[(50 + ev) * 16 + ti] ? tr[(50 + ev) * 16 + ti] - b0 : -1); printf("\n"); }
     {
       std::vector<long long> cr(4 * 1024); CK(cudaMemcpy(cr.data(), d_tr + 2048, cr.size() * 8, cudaMemcpyDeviceToHost));
       const int grid = a.n_tiles < 2 * sms ? a.n_tiles : 2 * sms;
