@@ -240,8 +240,8 @@ def fk_tree_frames(fk: FkDesc, q: torch.Tensor) -> torch.Tensor:
 def _is_batched(t) -> bool:
     """True inside a vmapped backward (``jacobian(vectorize=True)``, ``is_grads_batched``): such tensors have no storage a
     CUDA launch could read."""
-    try:
-        return bool(torch._C._functorch.is_batchedtensor(t))
+    try:  # both vmap implementations mark their tensors with a dispatch key (Batched / FuncTorchBatched)
+        return "Batched" in str(torch._C._dispatch_keys(t))
     except Exception:
         return False
 
@@ -299,6 +299,15 @@ class _ScoreFunction(torch.autograd.Function):
             _, jac = ctx.evaluator(q, _lib.DC_GRAD_JAC)
         # mul + sum (not einsum / bmm): both have batching rules, which the vmapped backward needs
         return (grad_score.to(jac.dtype).unsqueeze(-1) * jac).sum(-2), None
+
+
+def differentiable_score(q: torch.Tensor, evaluator) -> torch.Tensor:
+    """Run ``evaluator`` on q (any device / dtype handled by the evaluator) with autograd support."""
+    if q.requires_grad and torch.is_grad_enabled():
+        score, _ = _ScoreFunction.apply(q, evaluator)
+        return score
+    score, _ = evaluator(q, _lib.DC_GRAD_NONE)
+    return score
 
 
 class _FkFunction(torch.autograd.Function):
