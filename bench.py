@@ -510,6 +510,7 @@ def run_extras(args, torch, dist, lib, dev, rank, world, group, scorer, checker,
     del q5
     if world == 1:
         cfgs["cfg3"] = bench_cfg3(torch, lib, dev, timed, hbm_peak)
+        cfgs["wide_tc"] = bench_wide(torch, lib, dev, timed)
         cfgs["cfg4"] = bench_cfg4(torch, dev)
         cfgs["fit"] = bench_fit(torch, dev)
         # ---- the reference's own ATen code on this GPU (courtesy row: fused vs unfused on identical silicon) --------------
@@ -566,6 +567,43 @@ def bench_cfg3(torch, lib, dev, timed, hbm_peak):
             "roofline": {"bound": "hbm", "achieved": bytes_per_eval * b / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": bytes_per_eval * b / t / 1e9 / hbm_peak, "algorithmic_bytes_per_eval": bytes_per_eval},
             "algorithmic_tflops": flops * b / t / 1e12}
+
+
+def bench_wide(torch, lib, dev, timed):
+    """The tensor-core kernel's wide instantiation (15 <= F <= 30, one CTA per SM) on the reference tutorial's robot:
+    PandaFK (F = 21), 2000 SVs, 65536 queries, RQKernel — at the reference's default width (gamma = 10: metre-scale
+    features make the kernel wide, the dispatcher decides) and at a narrow width (gamma = 300), each against the FP32-pipe
+    kernels (tensor-core path switched off)."""
+    from diffco_b200 import DiffCo, _lib
+    from diffco_b200 import distributed as D
+    from diffco_b200 import kernel as K
+    from diffco_b200 import model as M
+
+    n, b = 2000, 65536
+    robot = M.PandaFK()
+    gen = torch.Generator().manual_seed(SEED)
+    lim = robot.limits.double()
+    Sc = torch.rand(n, 7, generator=gen, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+    W = torch.randn(n, generator=gen, dtype=torch.float64)
+    qd = (torch.rand(b, 7, generator=gen, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]).float().to(dev)
+    out = {"workload": "PandaFK (F = 21), 2000 SVs, batch 65536, RQKernel, score + gradient, fp32", "unit": UNIT}
+    tc_was = lib.dc_get_option(_lib.DC_OPT_TC_ENABLE)
+    try:
+        for gamma in (10.0, 300.0):
+            chk = DiffCo(kernel_func=K.RQKernel(gamma), transform=robot.fkine)
+            chk.support_points = Sc.float().to(dev)
+            chk.support_transformed = robot.fkine(chk.support_points)
+            chk.gains = W.float().to(dev)
+            sc = D.ShardedScorer(chk, weights="gains")
+            row = {}
+            for label, tc in (("dispatch", 1.0), ("fp32_pipe", 0.0)):
+                _lib.check(lib.dc_set_option(_lib.DC_OPT_TC_ENABLE, tc), "dc_set_option")
+                ms, _, _, _ = timed(lambda: sc.local_score_and_grad(qd), 10, 3, sc=None)
+                row[label] = {"value": b * 10 / (ms * 1e-3), "kernel": _lib.KERNEL_NAMES.get(lib.dc_last_score_kernel(), "?")}
+            out[f"gamma_{gamma:g}"] = row
+    finally:
+        lib.dc_set_option(_lib.DC_OPT_TC_ENABLE, tc_was)
+    return out
 
 
 def bench_cfg4(torch, dev):

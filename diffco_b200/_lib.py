@@ -21,7 +21,7 @@ DC_MAX_FEATURES = 64
 DC_MAX_TREE_NODES = 24
 DC_MAX_CLASSES = 8
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 DC_F32, DC_F64 = 0, 1
 DC_FK_NONE, DC_FK_PLANAR_CHAIN, DC_FK_SE2_BODY, DC_FK_SE3_BODY, DC_FK_DH_ARMS, DC_FK_SE2_BASE_PLANAR_ARM, DC_FK_JOINT_TREE = range(7)
 DC_JOINT_FIXED, DC_JOINT_REV_X, DC_JOINT_REV_Y, DC_JOINT_REV_Z, DC_JOINT_PRISMATIC = range(5)
@@ -145,7 +145,7 @@ PROTOTYPES = {
     "dc_pack_supports": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dc_supports_tc_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "dc_pack_supports_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(KernelDesc), C.c_void_p, C.c_void_p]),
-    "dc_supports_tc_info": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "dc_supports_tc_info": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "dc_set_option": (C.c_int, [C.c_int32, C.c_double]),
     "dc_get_option": (C.c_double, [C.c_int32]),
     "dc_last_score_kernel": (C.c_int, []),

@@ -284,7 +284,7 @@ static constexpr int64_t kTqMinBatch = 2048;
 
 static bool tq_feature_count(int f) {  // keep in sync with the switch in dc_score_tq_inst.cu
   switch (f) {
-    case 2: case 3: case 4: case 6: case 7: case 8: case 10: case 12: case 14: case 15: case 16:
+    case 2: case 3: case 4: case 6: case 7: case 8: case 10: case 12: case 14: case 15: case 16: case 21: case 24: case 27:
       return true;
     default:
       return false;

@@ -68,11 +68,11 @@ double tc_get_option(int option) {
 }
 
 static bool tc_shape_ok(int n_features, int n_class, int dtype) {
-  return dtype == DC_F32 && n_class == 1 && n_features >= 1 && n_features <= TcLayout::FMAX;
+  return dtype == DC_F32 && n_class == 1 && n_features >= 1 && n_features <= TcLayoutT<32>::FMAX;
 }
 
 // Does dc_score_grad send this call to the tensor-core kernel?  (DiffCo.score with RQKernel(p = 2), one class,
-// F <= 14, fp32, score or score + summed gradient, a batch large enough to fill the SMs, and — when the caller told us
+// F <= 30 (<= 14: two CTAs per SM, the BASELINE shape; 15..30: one CTA per SM), fp32, score or score + summed gradient, a batch large enough to fill the SMs, and — when the caller told us
 // max|s|^2 — a kernel narrow enough that only a small fraction of the pairs falls under the near-pair threshold.)
 bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel, const dc_supports& sv, int64_t batch,
                               int grad_mode) {
@@ -82,7 +82,7 @@ bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel
   if (fk.n_repeat > 1 || fk.time_last) return false;  // composite maps (line / temporal kernels): lane-split or thread-per-query
   if (kernel.kind != DC_K_RQ || kernel.order != 2 || !(kernel.param > 0)) return false;
   if ((float)kernel.param != (float)sv.tc_gamma) return false;  // the operand image has the kernel width folded in
-  if (fk.type != DC_FK_NONE && fk.dof > TcLayout::QS_DOF) return false;
+  if (fk.type != DC_FK_NONE && fk.dof > (tc_group(F) == 16 ? TcLayoutT<16>::QS_DOF : TcLayoutT<32>::QS_DOF)) return false;
   if (grad_mode != DC_GRAD_NONE && grad_mode != DC_GRAD_SUM) return false;
   if (batch < (int64_t)g_tc_min_batch || sv.n >= (1 << 24)) return false;
   if (sv.tc_s2max > 0) {
@@ -90,6 +90,8 @@ bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel
     const double drho = g_tc_err_coef * 1.5 * sv.tc_s2max;
     const double tcrit = std::cbrt(std::fmax(kernel.param * drho / g_tc_tol_pair, 1.0));
     const double thr = (tcrit - 1.0) / (kernel.param / 2.0);
+    // (measured for the wide instantiation too, bench.py configs.wide_tc: Panda at gamma = 10 has 11 % near pairs and the
+    // exact path then costs more than the whole lane-split kernel — 1.6e7 vs 3.4e7 evals/s — so the same limit applies)
     if (thr > 0.04 * sv.tc_s2max) return false;
   }
   return true;
@@ -152,7 +154,7 @@ extern "C" {
 int dc_supports_tc_bytes(int64_t n, int32_t n_features, int32_t n_class, int32_t dtype, int64_t* bytes) {
   if (n < 1 || !bytes) return DC_ERR_INVALID_ARG;
   if (!tc_shape_ok(n_features, n_class, dtype) || n >= (1 << 24)) return DC_ERR_UNSUPPORTED;
-  *bytes = (int64_t)tc_blob_bytes(n);
+  *bytes = (int64_t)tc_blob_bytes(n, tc_group(n_features));
   return DC_OK;
 }
 
@@ -165,10 +167,10 @@ int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_
                                  (float)kernel->param, static_cast<unsigned char*>(blob), (cudaStream_t)stream);
 }
 
-int dc_supports_tc_info(const void* blob, int64_t n, double* s2max, int32_t* valid) {
-  if (!blob || n < 1 || n >= (1 << 24)) return DC_ERR_INVALID_ARG;
+int dc_supports_tc_info(const void* blob, int64_t n, int32_t n_features, double* s2max, int32_t* valid) {
+  if (!blob || n < 1 || n >= (1 << 24) || !tc_shape_ok(n_features, 1, DC_F32)) return DC_ERR_INVALID_ARG;
   float t[TcLayout::TRAILER_FLOATS];
-  if (cudaMemcpy(t, tc_trailer(blob, n), sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) {  // synchronises (pack time)
+  if (cudaMemcpy(t, tc_trailer(blob, n, tc_group(n_features)), sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) {  // synchronises (pack time)
     (void)cudaGetLastError();
     return DC_ERR_CUDA;
   }

@@ -56,20 +56,26 @@
 
 namespace dc {
 
-struct TcLayout {
+// FG = K slots per operand group = 16 (F <= 14: the BASELINE shape, two CTAs per SM) or 32 (F <= 30: Panda, dual arms,
+// URDF robots; one CTA per SM).  Each of the three GEMM1 groups holds FG - 2 feature slots + 2 constant slots.
+template <int FG>
+struct TcLayoutT {
+  static_assert(FG == 16 || FG == 32, "operand group of 16 or 32 K slots");
   static constexpr int TM = 128;   // queries per tile == UMMA M
   static constexpr int NC = 96;    // support vectors per chunk == UMMA N of GEMM1
-  static constexpr int FMAX = 14;  // features
-  static constexpr int K1 = 48;    // GEMM1 K slots
-  static constexpr int N2 = 32;    // GEMM2 N: [w s (14), w, 0 | corrections (14), w correction, 0]
-  static constexpr int ONES_ROW = 14;
+  static constexpr int GRP = FG;
+  static constexpr int FMAX = FG - 2;  // features
+  static constexpr int K1 = 3 * FG;    // GEMM1 K slots
+  static constexpr int N2 = 2 * FG;    // GEMM2 N: [w s (FMAX), w, 0 | corrections (FMAX), w correction, 0]
+  static constexpr int ONES_ROW = FG - 2;
   static constexpr int KS2 = NC / 8;  // GEMM2 instructions per chunk (8 supports x {ch, cl} each)
+  static constexpr int CTAS_PER_SM = FG == 16 ? 2 : 1;
   // operand images (bytes).  Global layout: [n_chunks x B1][n_chunks x B2W][trailer]; a B2W record is the GEMM2 image
   // followed by the chunk's fp32 weights [NC] and its max|s|^2.  (Reading the weights through the L1 instead was
   // measured: with 2 x 112 KB of shared memory only 28 KB of L1 remain, 15 % of those loads missed and showed up as
   // the kernel's top stall, profiles/r02o_*.)
-  static constexpr int B1_BYTES = NC * K1 * 2;        // [K1/8][NC][8] f16           9216
-  static constexpr int B2_STEP_BYTES = N2 * 16 * 2;   // per 8 supports: [2][32][8]  1024
+  static constexpr int B1_BYTES = NC * K1 * 2;        // [K1/8][NC][8] f16           9216 (FG 16)
+  static constexpr int B2_STEP_BYTES = N2 * 16 * 2;   // per 8 supports: [2][N2][8]  1024
   static constexpr int B2_BYTES = KS2 * B2_STEP_BYTES;  // 12288
   static constexpr int OFF_W = B2_BYTES;              // fp32 weights [NC], then the chunk's max |s|^2
   static constexpr int META_S2MAX = NC;               // float index in the weight section
@@ -78,9 +84,12 @@ struct TcLayout {
   //                 3 Sa  4 tau c0  5 tau  6 1/(2^15 Sg)  7 gamma  8 valid (1.0 / 0.0)  9 1/(tau c0)
   static constexpr int TRAILER_FLOATS = 16;
   static constexpr int RS1 = 2, RS2 = 2;    // ring slots (both indexed by chunk parity, like the TMEM stages)
-  // TMEM columns: two T / CC stages, two G accumulators (tile parity)
+  // TMEM columns: two T / CC stages, then the G accumulator(s): two (tile parity) of 32 columns for FG 16, one of 64
+  // for FG 32 — GEMM2 of the next tile cannot start before every owner has read G (it waits for all 256 query threads'
+  // cc of chunk 0, and the owners only get there after their epilogue), so one accumulator is enough
   static constexpr int COL_STAGE = NC;
-  static constexpr int COL_G = 2 * COL_STAGE;  // 192 .. 223, 224 .. 255
+  static constexpr int COL_G = 2 * COL_STAGE;  // 192 ..
+  static constexpr int G_BUFS = FG == 16 ? 2 : 1;
   static constexpr int TMEM_COLS = 256;
   // near-pair queue entries per warp: large enough that queues are normally drained once, at the end of the tile — a
   // drain in the middle of the chunk loop stalls its warp for ~1500 cycles and, through the chunk barriers, the whole CTA
@@ -89,7 +98,7 @@ struct TcLayout {
   static constexpr int QTHREADS = QWARPS * 32;
   static constexpr int CTRL_WARP = QWARPS;
   static constexpr int THREADS = QTHREADS + 128;
-  static constexpr int QS_DOF = 8;   // staged configurations: dof <= 8 for real feature maps (FK NONE needs none)
+  static constexpr int QS_DOF = FG == 16 ? 8 : 16;   // staged configurations (FK NONE needs none)
   // shared memory (bytes)
   static constexpr int SM_BAR = 0;
   static constexpr int SM_TRAILER = 136;    // the blob's trailer floats 0..11, copied once per CTA (bytes 136 .. 184)
@@ -99,20 +108,23 @@ struct TcLayout {
   static constexpr int SM_RING1 = 256;
   static constexpr int SM_RING2 = SM_RING1 + RS1 * B1_BYTES;
   static constexpr int SM_A = SM_RING2 + RS2 * B2W_BYTES;   // A [K1/8][128][8] f16
-  static constexpr int SM_XS = SM_A + TM * K1 * 2;          // features [2][128][16] f32 (near-pair path, epilogue)
+  static constexpr int SM_XS = SM_A + TM * K1 * 2;          // features [2][128][FG] f32 (near-pair path, epilogue)
   static constexpr int XLO_SCALE_LOG2 = 22;                 // low parts are kept as f16 of 2^22 lo (|lo| <= ulp(hi) / 2)
-  // exact-path accumulators: score [8][32], feature gradient [8][32][16] (non-owner warps first); the owners' half
-  // (+ 512 bytes) doubles as the output records [128][17] once the owners have read it
-  static constexpr int SM_XLO = SM_XS + 2 * TM * 16 * 4;    // low parts of the features [2][128][16] f16 (near-pair path)
-  static constexpr int SM_ACC = SM_XLO + 2 * TM * 16 * 2;
-  static constexpr int ACC_BYTES = QWARPS * 32 * 4 + QWARPS * 32 * 16 * 4 + 512;
+  // exact-path accumulators: score [8][32], feature gradient [8][32][FG] (non-owner warps first); the owners' half
+  // (+ 512 bytes) doubles as the output records [128][dof + 1] once the owners have read it
+  static constexpr int SM_XLO = SM_XS + 2 * TM * FG * 4;    // low parts of the features [2][128][FG] f16 (near-pair path)
+  static constexpr int SM_ACC = SM_XLO + 2 * TM * FG * 2;
+  static constexpr int ACC_BYTES = QWARPS * 32 * 4 + QWARPS * 32 * FG * 4 + 512;
   static constexpr int SM_QS = SM_ACC + ACC_BYTES;          // staged configurations [2][128][QS_DOF]
   static constexpr int SM_ROWS = SM_QS + 2 * TM * QS_DOF * 4;
   static constexpr int SM_QUEUE = SM_ROWS + 5 * TM * 4;   // lower-half partial scores [128], near-threshold line [2][128] x 2
   static constexpr int SM_BYTES = SM_QUEUE + QWARPS * QCAP * 4;
+  static_assert(CTAS_PER_SM * (SM_BYTES + 1024) <= 233472, "the CTAs of one SM must fit in 228 KB of shared memory");
+  static_assert(SM_BYTES <= 232448, "at most 227 KB of dynamic shared memory per CTA");
+  static_assert(TM * (DC_MAX_DOF + 1) * 4 <= 4 * 32 * FG * 4 + 512, "output records must fit the owners' accumulators");
 };
-static_assert(2 * (TcLayout::SM_BYTES + 1024) <= 233472, "two CTAs per SM must fit in 228 KB of shared memory");
-static_assert(TcLayout::TM * (DC_MAX_DOF + 1) * 4 <= 4 * 32 * 16 * 4 + 512, "output records must fit the owners' accumulators");
+using TcLayout = TcLayoutT<16>;
+__host__ __device__ constexpr int tc_group(int n_features) { return n_features <= 14 ? 16 : 32; }
 
 struct TcArgs {
   dc_fk_desc fk;
@@ -286,12 +298,17 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 __device__ __forceinline__ float pow2_floor(float v) { return __uint_as_float(__float_as_uint(v) & 0x7f800000u); }
 
 __host__ __device__ inline int tc_n_chunks(long long n_sv) { return (int)((n_sv + TcLayout::NC - 1) / TcLayout::NC); }
-__host__ __device__ inline size_t tc_trailer_offset(long long n_sv) {
-  return (size_t)tc_n_chunks(n_sv) * (TcLayout::B1_BYTES + TcLayout::B2W_BYTES);
+// fg: the operand group size the image was packed for (tc_group(n_features))
+__host__ __device__ inline size_t tc_trailer_offset(long long n_sv, int fg = 16) {
+  const size_t per_chunk = fg == 16 ? (size_t)(TcLayoutT<16>::B1_BYTES + TcLayoutT<16>::B2W_BYTES)
+                                    : (size_t)(TcLayoutT<32>::B1_BYTES + TcLayoutT<32>::B2W_BYTES);
+  return (size_t)tc_n_chunks(n_sv) * per_chunk;
 }
-__host__ __device__ inline size_t tc_blob_bytes(long long n_sv) { return tc_trailer_offset(n_sv) + TcLayout::TRAILER_FLOATS * 4; }
-__host__ __device__ inline const float* tc_trailer(const void* blob, long long n_sv) {
-  return reinterpret_cast<const float*>(static_cast<const unsigned char*>(blob) + tc_trailer_offset(n_sv));
+__host__ __device__ inline size_t tc_blob_bytes(long long n_sv, int fg = 16) {
+  return tc_trailer_offset(n_sv, fg) + TcLayout::TRAILER_FLOATS * 4;
+}
+__host__ __device__ inline const float* tc_trailer(const void* blob, long long n_sv, int fg = 16) {
+  return reinterpret_cast<const float*>(static_cast<const unsigned char*>(blob) + tc_trailer_offset(n_sv, fg));
 }
 
 // ---- pack: support vectors -> operand images ----------------------------------------------------------------------
@@ -339,10 +356,11 @@ __device__ __forceinline__ TcScales tc_scales(const float* trailer, float gamma)
 
 // One thread per (chunk, local support index).  s_feat[N, F] are the transformed supports, w[N] the weights.  The whole
 // blob was zeroed by the caller (the chunk maxima are accumulated with atomicMax).
+template <int FG>
 __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __restrict__ s, const float* __restrict__ w,
                                                                  int n, int F, int n_chunks, float gamma,
                                                                  unsigned char* __restrict__ blob) {
-  using L = TcLayout;
+  using L = TcLayoutT<FG>;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_chunks * L::NC) return;
   unsigned char* blob2 = blob + (size_t)n_chunks * L::B1_BYTES;
@@ -358,44 +376,47 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
     trailer[9] = 1.f / sc.tc0;
   }
   const int j = idx / L::NC, r = idx - j * L::NC;
-  float b1[L::K1], mainv[16], corrv[16];
+  float b1[L::K1], mainv[FG], corrv[FG];
 #pragma unroll
   for (int k = 0; k < L::K1; ++k) b1[k] = 0.f;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) mainv[k] = corrv[k] = 0.f;
+  for (int k = 0; k < FG; ++k) mainv[k] = corrv[k] = 0.f;
   float wv = 0.f;
   float* w_sec = reinterpret_cast<float*>(blob2 + (size_t)j * L::B2W_BYTES + L::OFF_W);
   if (idx < n) {
     wv = w[idx];
     const float gw = sc.sg * wv;  // exact (power of two)
     float ss = 0.f;
-    for (int f = 0; f < F; ++f) {
-      const float sv = s[(size_t)idx * F + f];
-      const float m = sc.beta * sv;  // (-2 tau c0 / Sa) s
-      const float hi = split_hi(m);
-      b1[f] = hi;                        // pairs with xh
-      b1[16 + f] = hi * (1.f / 256.f);   // pairs with 256 xl
-      b1[32 + f] = (m - hi) * 256.f;     // pairs with xh / 256
-      const float p = gw * sv;
-      const float ph = split_hi(p);
-      mainv[f] = ph;
-      corrv[f] = p - ph;
-      ss = fmaf(sv, sv, ss);
+#pragma unroll
+    for (int f = 0; f < L::FMAX; ++f) {
+      if (f < F) {
+        const float sv = s[(size_t)idx * F + f];
+        const float m = sc.beta * sv;  // (-2 tau c0 / Sa) s
+        const float hi = split_hi(m);
+        b1[f] = hi;                          // pairs with xh
+        b1[FG + f] = hi * (1.f / 256.f);     // pairs with 256 xl
+        b1[2 * FG + f] = (m - hi) * 256.f;   // pairs with xh / 256
+        const float p = gw * sv;
+        const float ph = split_hi(p);
+        mainv[f] = ph;
+        corrv[f] = p - ph;
+        ss = fmaf(sv, sv, ss);
+      }
     }
     const float S = fmaf(sc.tc0, ss, sc.tau);  // tau (1 + c0 |s|^2)
     const float s1 = split_hi(S), s2 = split_hi(S - s1), s3 = S - s1 - s2;
-    b1[14] = s1;   // x 1
-    b1[15] = s2;   // x 1
-    b1[30] = s3;   // x 1
-    b1[31] = 1.f;  // x X1   (X = tau c0 |x|^2, three terms)
-    b1[46] = 1.f;  // x X2
-    b1[47] = 1.f;  // x X3
+    b1[FG - 2] = s1;       // x 1
+    b1[FG - 1] = s2;       // x 1
+    b1[2 * FG - 2] = s3;   // x 1
+    b1[2 * FG - 1] = 1.f;  // x X1   (X = tau c0 |x|^2, three terms)
+    b1[3 * FG - 2] = 1.f;  // x X2
+    b1[3 * FG - 1] = 1.f;  // x X3
     const float gh = split_hi(gw);
     mainv[L::ONES_ROW] = gh;
     corrv[L::ONES_ROW] = gw - gh;
     atomicMax(reinterpret_cast<int*>(w_sec) + L::META_S2MAX, __float_as_int(ss));
   } else {
-    b1[14] = 32768.f;  // padding rows: T >= 2^15, never near; weight 0 removes them from every sum
+    b1[FG - 2] = 32768.f;  // padding rows: T >= 2^15, never near; weight 0 removes them from every sum
   }
   __half* b1p = reinterpret_cast<__half*>(blob + (size_t)j * L::B1_BYTES);
 #pragma unroll
@@ -404,12 +425,12 @@ __global__ void __launch_bounds__(128) pack_supports_tc_kernel(const float* __re
   __half* b2p = reinterpret_cast<__half*>(blob2 + (size_t)j * L::B2W_BYTES + (r >> 3) * L::B2_STEP_BYTES);
   const int i = r & 7;
 #pragma unroll
-  for (int f = 0; f < 16; ++f) {
+  for (int f = 0; f < FG; ++f) {
     const __half hm = __float2half_rn(mainv[f]);
-    b2p[0 * (L::N2 * 8) + f * 8 + i] = hm;                               // slot i,     row f:      (Sg w s)_h (row 14: (Sg w)_h)
-    b2p[1 * (L::N2 * 8) + f * 8 + i] = hm;                               // slot 8 + i, row f
-    b2p[0 * (L::N2 * 8) + (16 + f) * 8 + i] = __float2half_rn(corrv[f]);  // slot i,     row 16 + f: low parts
-    b2p[1 * (L::N2 * 8) + (16 + f) * 8 + i] = __float2half_rn(0.f);
+    b2p[0 * (L::N2 * 8) + f * 8 + i] = hm;                                // slot i,     row f:      (Sg w s)_h (row FG - 2: (Sg w)_h)
+    b2p[1 * (L::N2 * 8) + f * 8 + i] = hm;                                // slot 8 + i, row f
+    b2p[0 * (L::N2 * 8) + (FG + f) * 8 + i] = __float2half_rn(corrv[f]);  // slot i,     row FG + f: low parts
+    b2p[1 * (L::N2 * 8) + (FG + f) * 8 + i] = __float2half_rn(0.f);
   }
   w_sec[r] = wv;
 }
@@ -439,26 +460,27 @@ enum { TCB_FK = 1, TCB_EPI = 2, TCB_OWN = 3, TCB_LOW = 4, TCB_ACC = 5, TCB_END =
 // always a single round), so a row's result depends neither on its position in the batch nor on timing.
 // (Out of line, and it re-derives its shared-memory pointers from (warp, tile parity): the chunk loop that calls it keeps
 // as little state alive across the call as possible.)
+template <int FG>
 __device__ __noinline__ void tc_drain_pairs(const TcArgs& a, int count, int warp, int buf) {
-  using L = TcLayout;
-  constexpr int FM = TcLayout::FMAX;
+  using L = TcLayoutT<FG>;
+  constexpr int FM = L::FMAX;
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const uint32_t* queue = reinterpret_cast<const uint32_t*>(smem + L::SM_QUEUE) + warp * L::QCAP;
-  const float* xs = reinterpret_cast<const float*>(smem + L::SM_XS) + buf * L::TM * 16;
-  const __half* xlo = reinterpret_cast<const __half*>(smem + L::SM_XLO) + buf * L::TM * 16;
+  const float* xs = reinterpret_cast<const float*>(smem + L::SM_XS) + buf * L::TM * FG;
+  const __half* xlo = reinterpret_cast<const __half*>(smem + L::SM_XLO) + buf * L::TM * FG;
   float* sacc_w = reinterpret_cast<float*>(smem + L::SM_ACC) + warp * 32;
-  float* gacc_w = reinterpret_cast<float*>(smem + L::SM_ACC) + L::QWARPS * 32 + warp * 32 * 16;
-  const float lo_scale = 1.f / (float)(1 << TcLayout::XLO_SCALE_LOG2);
+  float* gacc_w = reinterpret_cast<float*>(smem + L::SM_ACC) + L::QWARPS * 32 + warp * 32 * FG;
+  const float lo_scale = 1.f / (float)(1 << L::XLO_SCALE_LOG2);
   for (int head = 0; head < count; head += 32) {
     const bool valid = head + lane < count;
     const uint32_t e = queue[valid ? head + lane : head];
     const int row = (int)(e >> 24), n = (int)(e & 0xffffffu);
     const float4* tr = reinterpret_cast<const float4*>(a.table + (size_t)n * a.row_stride);  // 16-byte aligned rows
-    const float4* xr = reinterpret_cast<const float4*>(xs + row * 16);
-    float t[16], x[16];
+    const float4* xr = reinterpret_cast<const float4*>(xs + row * FG);
+    float t[FG], x[FG];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
+    for (int v = 0; v < FG / 4; ++v) {
       const float4 tv = (4 * v < a.row_stride) ? tr[v] : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 xv = xr[v];
       t[4 * v] = tv.x, t[4 * v + 1] = tv.y, t[4 * v + 2] = tv.z, t[4 * v + 3] = tv.w;
@@ -466,33 +488,36 @@ __device__ __noinline__ void tc_drain_pairs(const TcArgs& a, int count, int warp
     }
     float wv = 0.f;
 #pragma unroll
-    for (int f = 0; f < 16; ++f) wv = (f == a.f_pad) ? t[f] : wv;  // the weight sits right after the padded features
+    for (int f = 0; f < FG; ++f) wv = (f == a.f_pad) ? t[f] : wv;  // the weight sits right after the padded features
     // low parts: x = x_hi + x_lo and s = s_hi + s_lo from the float64 feature map, so that the difference is good to ~1e-9
     // even when the pair is 1e-3 apart (a float32 feature alone is off by up to half an ulp of ITS magnitude)
-    float lo[16];
+    float lo[FG];
     {
-      const uint4* lr = reinterpret_cast<const uint4*>(xlo + row * 16);
-      const uint4 l0 = lr[0], l1 = lr[1];
-      const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+      const uint4* lr = reinterpret_cast<const uint4*>(xlo + row * FG);
 #pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&lw[v]));
-        lo[2 * v] = p.x * lo_scale;
-        lo[2 * v + 1] = p.y * lo_scale;
+      for (int q4 = 0; q4 < FG / 8; ++q4) {
+        const uint4 l = lr[q4];
+        const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&lw[v]));
+          lo[8 * q4 + 2 * v] = p.x * lo_scale;
+          lo[8 * q4 + 2 * v + 1] = p.y * lo_scale;
+        }
       }
     }
     if (a.table_lo != nullptr) {
       const float4* tl = reinterpret_cast<const float4*>(a.table_lo + (size_t)n * a.row_stride);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
+      for (int v = 0; v < FG / 4; ++v) {
         const float4 tv = (4 * v < a.row_stride) ? tl[v] : make_float4(0.f, 0.f, 0.f, 0.f);
         lo[4 * v] += tv.x, lo[4 * v + 1] += tv.y, lo[4 * v + 2] += tv.z, lo[4 * v + 3] += tv.w;
       }
     }
-    float d[FM], rho = 0.f;
+    float d[FG], rho = 0.f;
 #pragma unroll
-    for (int f = 0; f < FM; ++f) {
-      d[f] = (f < a.n_feat) ? (x[f] + t[f]) + lo[f] : 0.f;
+    for (int f = 0; f < FG; ++f) {
+      d[f] = (f < FM && f < a.n_feat) ? (x[f] + t[f]) + lo[f] : 0.f;
       rho = fmaf(d[f], d[f], rho);
     }
     float k, coef;
@@ -505,14 +530,14 @@ __device__ __noinline__ void tc_drain_pairs(const TcArgs& a, int count, int warp
     uint32_t pending = __ballot_sync(0xffffffffu, valid);
     while (pending != 0) {
       if (valid && turn == 0) {
-        float4* g4 = reinterpret_cast<float4*>(gacc_w + r * 16);
+        float4* g4 = reinterpret_cast<float4*>(gacc_w + r * FG);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < FG / 4; ++v) {
           float4 g = g4[v];
-          if (4 * v + 0 < FM) g.x = fmaf(cg, d[4 * v + 0 < FM ? 4 * v + 0 : 0], g.x);
-          if (4 * v + 1 < FM) g.y = fmaf(cg, d[4 * v + 1 < FM ? 4 * v + 1 : 0], g.y);
-          if (4 * v + 2 < FM) g.z = fmaf(cg, d[4 * v + 2 < FM ? 4 * v + 2 : 0], g.z);
-          if (4 * v + 3 < FM) g.w = fmaf(cg, d[4 * v + 3 < FM ? 4 * v + 3 : 0], g.w);
+          g.x = fmaf(cg, d[4 * v + 0], g.x);  // d is zero past the features
+          g.y = fmaf(cg, d[4 * v + 1], g.y);
+          g.z = fmaf(cg, d[4 * v + 2], g.z);
+          g.w = fmaf(cg, d[4 * v + 3], g.w);
           g4[v] = g;
         }
         sacc_w[r] += cs;
@@ -528,8 +553,9 @@ __device__ __noinline__ void tc_drain_pairs(const TcArgs& a, int count, int warp
 // ---- lower half of the query warps: configurations of tile ti -> FK (float64) -> features (hi, lo), |x|^2, A operand ----------
 // Out of line on purpose: its register needs (float64 sincos chain) must not leak into the allocation of the chunk loop.
 // It re-derives what it needs (tile range, scales) instead of taking it from the caller, for the same reason.
+template <int FG>
 __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
-  using L = TcLayout;
+  using L = TcLayoutT<FG>;
   constexpr int NC = L::NC, FM = L::FMAX, QT = L::QTHREADS, TM = L::TM;
   (void)NC;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -555,14 +581,14 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
   const int buf = ti & 1;
   const long long b_base = (t0 + ti) * TM;
   const int nq = (int)min((long long)TM, a.batch - b_base);
-  float* xs = xs_all + buf * TM * 16;
+  float* xs = xs_all + buf * TM * FG;
   float* qs = qs_all + buf * TM * L::QS_DOF;
   const float* src = a.q + (size_t)b_base * a.n_in;
   const int n_words = nq * a.n_in;
   float xx = 0.f, xamax = 0.f;
   bool in_range;
   const float xlo_sc = (float)(1 << L::XLO_SCALE_LOG2);
-  if (has_fk && a.fk.type == DC_FK_PLANAR_CHAIN && a.fk.n_repeat <= 1 && !a.fk.time_last) {
+  if (FG == 16 && has_fk && a.fk.type == DC_FK_PLANAR_CHAIN && a.fk.n_repeat <= 1 && !a.fk.time_last) {
     // The BASELINE robot.  One ROLLED loop over the joints that writes features, low parts and the A-operand words
     // straight to shared memory: this stage runs once per tile on four warps, its code is cold every time, and as
     // 1150 unrolled instructions it spent half its cycles waiting for instruction fetches (ncu: stall_no_inst, 53 % of
@@ -574,10 +600,12 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
 #pragma unroll
     for (int kc = 0; kc < L::K1 / 8; ++kc) reinterpret_cast<uint4*>(a_op)[kc * TM + row] = z4;
     {
-      uint4* xr = reinterpret_cast<uint4*>(xs + row * 16);
-      xr[0] = z4, xr[1] = z4, xr[2] = z4, xr[3] = z4;
-      uint4* lr = reinterpret_cast<uint4*>(xlo_all + (buf * TM + row) * 16);
-      lr[0] = z4, lr[1] = z4;
+      uint4* xr = reinterpret_cast<uint4*>(xs + row * FG);
+#pragma unroll
+      for (int v = 0; v < FG / 4; ++v) xr[v] = z4;
+      uint4* lr = reinterpret_cast<uint4*>(xlo_all + (buf * TM + row) * FG);
+#pragma unroll
+      for (int v = 0; v < FG / 8; ++v) lr[v] = z4;
     }
     const int nl = (row < nq) ? a.fk.n_links : 0;
     const float* qr = qs + row * a.n_in;
@@ -594,8 +622,8 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
       py = fma(len, sn, py);
       const float hx = (float)px, hy = (float)py;
       const float lx = (float)(px - (double)hx), ly = (float)(py - (double)hy);
-      *reinterpret_cast<float2*>(xs + row * 16 + 2 * i) = make_float2(hx, hy);
-      reinterpret_cast<uint32_t*>(xlo_all + (buf * TM + row) * 16)[i] = pack_f16x2(lx * xlo_sc, ly * xlo_sc);
+      *reinterpret_cast<float2*>(xs + row * FG + 2 * i) = make_float2(hx, hy);
+      reinterpret_cast<uint32_t*>(xlo_all + (buf * TM + row) * FG)[i] = pack_f16x2(lx * xlo_sc, ly * xlo_sc);
       xx = fmaf(hx, hx, xx);
       xx = fmaf(hy, hy, xx);
       xamax = fmaxf(xamax, fmaxf(fabsf(hx), fabsf(hy)));
@@ -604,8 +632,8 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
       const float hix = split_hi(ax), hiy = split_hi(ay);
       unsigned char* aw = arow + ((2 * i) >> 3) * (TM * 16) + ((2 * i) & 7) * 2;
       *reinterpret_cast<uint32_t*>(aw) = pack_f16x2(hix, hiy);
-      *reinterpret_cast<uint32_t*>(aw + 2 * (TM * 16)) = pack_f16x2((ax - hix) * 256.f, (ay - hiy) * 256.f);
-      *reinterpret_cast<uint32_t*>(aw + 4 * (TM * 16)) = pack_f16x2(hix * (1.f / 256.f), hiy * (1.f / 256.f));
+      *reinterpret_cast<uint32_t*>(aw + (FG / 8) * (TM * 16)) = pack_f16x2((ax - hix) * 256.f, (ay - hiy) * 256.f);
+      *reinterpret_cast<uint32_t*>(aw + (2 * FG / 8) * (TM * 16)) = pack_f16x2(hix * (1.f / 256.f), hiy * (1.f / 256.f));
     }
     DC_TC_TRACE_TILE(0, 5);
     // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
@@ -616,9 +644,10 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
     }
     const float XX = in_range ? tc0 * xx : 0.f;
     const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
-    *reinterpret_cast<uint32_t*>(arow + 1 * (TM * 16) + 12) = pack_f16x2(1.f, 1.f);  // slots 14, 15: x S1, x S2
-    *reinterpret_cast<uint32_t*>(arow + 3 * (TM * 16) + 12) = pack_f16x2(1.f, x1);   // slots 30, 31: x S3, x 1
-    *reinterpret_cast<uint32_t*>(arow + 5 * (TM * 16) + 12) = pack_f16x2(x2, x3);    // slots 46, 47: x 1, x 1
+    // the two constant slots that close each group of FG: x S1, x S2 | x S3, x 1 | x 1, x 1
+    *reinterpret_cast<uint32_t*>(arow + (FG / 8 - 1) * (TM * 16) + 12) = pack_f16x2(1.f, 1.f);
+    *reinterpret_cast<uint32_t*>(arow + (2 * FG / 8 - 1) * (TM * 16) + 12) = pack_f16x2(1.f, x1);
+    *reinterpret_cast<uint32_t*>(arow + (3 * FG / 8 - 1) * (TM * 16) + 12) = pack_f16x2(x2, x3);
   } else {
     float x[FM], xlo[FM];  // features as float32 (hi, lo) pairs of a float64 evaluation (dc_fk.cuh: fk_forward_f32x)
     float qv[DC_MAX_DOF];
@@ -629,9 +658,9 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
 #pragma unroll
       for (int i = 0; i < DC_MAX_DOF; ++i) qv[i] = (row < nq && i < a.n_in) ? qs[row * a.n_in + i] : 0.f;
       {
-        float xh16[DC_MAX_DOF], xl16[DC_MAX_DOF];
+        float xh16[FG], xl16[FG];
 #pragma unroll
-        for (int i = 0; i < DC_MAX_DOF; ++i) xh16[i] = xl16[i] = 0.f;
+        for (int i = 0; i < FG; ++i) xh16[i] = xl16[i] = 0.f;
         if (row < nq) fk_forward_f32x<true>(a.fk, qv, xh16, 1, xl16, 1);
 #pragma unroll
         for (int f = 0; f < FM; ++f) {
@@ -641,30 +670,31 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
       }
     } else {
       // transform=None: the rows ARE the features; staged straight into the feature layout [128][16]
-      for (int i = tid; i < TM * 16; i += TM) xs[i] = 0.f;
+      for (int i = tid; i < TM * FG; i += TM) xs[i] = 0.f;
       named_sync(TCB_LOW, TM);
       for (int i = tid; i < n_words; i += TM) {
         const int r = i / a.n_in;
-        xs[r * 16 + (i - r * a.n_in)] = src[i];
+        xs[r * FG + (i - r * a.n_in)] = src[i];
       }
       named_sync(TCB_LOW, TM);
 #pragma unroll
       for (int f = 0; f < FM; ++f) {
-        x[f] = xs[row * 16 + f];
+        x[f] = xs[row * FG + f];
         xlo[f] = 0.f;
       }
     }
     DC_TC_TRACE_TILE(0, 5);
     {
       const float sc = (float)(1 << L::XLO_SCALE_LOG2);
-      uint4* lr = reinterpret_cast<uint4*>(xlo_all + (buf * TM + row) * 16);
-      uint4 l0, l1;
-      l0.x = pack_f16x2(xlo[0] * sc, xlo[1] * sc), l0.y = pack_f16x2(xlo[2] * sc, xlo[3] * sc);
-      l0.z = pack_f16x2(xlo[4] * sc, xlo[5] * sc), l0.w = pack_f16x2(xlo[6] * sc, xlo[7] * sc);
-      l1.x = pack_f16x2(xlo[8] * sc, xlo[9] * sc), l1.y = pack_f16x2(xlo[10] * sc, xlo[11] * sc);
-      l1.z = pack_f16x2(xlo[12] * sc, xlo[13] * sc), l1.w = 0u;
-      lr[0] = l0;
-      lr[1] = l1;
+      uint4* lr = reinterpret_cast<uint4*>(xlo_all + (buf * TM + row) * FG);
+      auto lo_at = [&](int f) { return f < FM ? xlo[f < FM ? f : 0] * sc : 0.f; };
+#pragma unroll
+      for (int v = 0; v < FG / 8; ++v) {
+        uint4 l;
+        l.x = pack_f16x2(lo_at(8 * v + 0), lo_at(8 * v + 1)), l.y = pack_f16x2(lo_at(8 * v + 2), lo_at(8 * v + 3));
+        l.z = pack_f16x2(lo_at(8 * v + 4), lo_at(8 * v + 5)), l.w = pack_f16x2(lo_at(8 * v + 6), lo_at(8 * v + 7));
+        lr[v] = l;
+      }
     }
 #pragma unroll
     for (int f = 0; f < FM; ++f) {
@@ -672,11 +702,10 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
       xamax = fmaxf(xamax, fabsf(x[f]));
     }
     {
-      float4* xr = reinterpret_cast<float4*>(xs + row * 16);
-      xr[0] = make_float4(x[0], x[1], x[2], x[3]);
-      xr[1] = make_float4(x[4], x[5], x[6], x[7]);
-      xr[2] = make_float4(x[8], x[9], x[10], x[11]);
-      xr[3] = make_float4(x[12], x[13], 0.f, 0.f);
+      float4* xr = reinterpret_cast<float4*>(xs + row * FG);
+      auto x_at = [&](int f) { return f < FM ? x[f < FM ? f : 0] : 0.f; };
+#pragma unroll
+      for (int v = 0; v < FG / 4; ++v) xr[v] = make_float4(x_at(4 * v), x_at(4 * v + 1), x_at(4 * v + 2), x_at(4 * v + 3));
     }
     // queries whose scaled features leave f16's range take the exact path for every pair (A row zeroed)
     in_range = (sa * xamax < 32768.f) && (tc0 * xx < 32768.f);
@@ -689,17 +718,17 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
       for (int f = 0; f < FM; ++f) {
         const float xsc = in_range ? sa * x[f] : 0.f;
         const float hi = split_hi(xsc);
-        v[f] = hi;                       // x beta s_h
-        v[16 + f] = (xsc - hi) * 256.f;  // x beta s_h / 256
-        v[32 + f] = hi * (1.f / 256.f);  // x 256 (beta s)_lo
+        v[f] = hi;                           // x beta s_h
+        v[FG + f] = (xsc - hi) * 256.f;      // x beta s_h / 256
+        v[2 * FG + f] = hi * (1.f / 256.f);  // x 256 (beta s)_lo
       }
       const float x1 = split_hi(XX), x2 = split_hi(XX - x1), x3 = XX - x1 - x2;
-      v[14] = 1.f;  // x S1   (S = tau (1 + c0 |s|^2), three terms)
-      v[15] = 1.f;  // x S2
-      v[30] = 1.f;  // x S3
-      v[31] = x1;   // x 1
-      v[46] = x2;   // x 1
-      v[47] = x3;   // x 1
+      v[FG - 2] = 1.f;      // x S1   (S = tau (1 + c0 |s|^2), three terms)
+      v[FG - 1] = 1.f;      // x S2
+      v[2 * FG - 2] = 1.f;  // x S3
+      v[2 * FG - 1] = x1;   // x 1
+      v[3 * FG - 2] = x2;   // x 1
+      v[3 * FG - 1] = x3;   // x 1
 #pragma unroll
       for (int kc = 0; kc < L::K1 / 8; ++kc) {
         uint4 pk;
@@ -729,7 +758,7 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
 #ifdef DC_TC_ENABLE_TRACE
   if (a.dbg != nullptr && t0 + ti == 0) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) a.dbg[(size_t)TM * (nch * NC) + TM * 32 + row * 16 + c] = c < FM ? xs[row * 16 + c] : 0.f;
+    for (int c = 0; c < 16; ++c) a.dbg[(size_t)TM * (nch * NC) + TM * 32 + row * 16 + c] = c < FM ? xs[row * FG + c] : 0.f;
   }
 #endif
   named_arrive(TCB_FK, QT);  // features, |x|^2 (and the staged configurations) of tile ti are visible to the owners
@@ -738,9 +767,9 @@ __device__ __noinline__ void tc_fk_stage(const TcArgs& a, int ti, int tid) {
 // ---- epilogue of tile ti (owner half of the query warps): G from TMEM, feature gradient, J_FK^T, records -> memory -----------
 // Out of line like tc_fk_stage: its register arrays must not shape the allocation of the chunk loop.  `sc_hi` is the
 // caller's partial score (upper column half); everything else is re-derived.
-template <int MODE>
+template <int MODE, int FG>
 __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, float sc_hi) {
-  using L = TcLayout;
+  using L = TcLayoutT<FG>;
   constexpr int NC = L::NC, FM = L::FMAX, QT = L::QTHREADS, TM = L::TM;
   (void)NC;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -750,12 +779,12 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
   uint64_t* bar_g = reinterpret_cast<uint64_t*>(smem + L::SM_BAR) + 11;
   const uint32_t tmem = *reinterpret_cast<const uint32_t*>(smem + L::SM_TMEM_SLOT);
   const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const float* xs = reinterpret_cast<const float*>(smem + L::SM_XS) + buf * TM * 16;
+  const float* xs = reinterpret_cast<const float*>(smem + L::SM_XS) + buf * TM * FG;
   float* sacc = reinterpret_cast<float*>(smem + L::SM_ACC);
   float* gacc = sacc + L::QWARPS * 32;
-  float* os = gacc + 4 * 32 * 16;
+  float* os = gacc + 4 * 32 * FG;
   float* sacc_w = sacc + warp * 32;
-  float* gacc_w = gacc + warp * 32 * 16;
+  float* gacc_w = gacc + warp * 32 * FG;
   float* qs_all = reinterpret_cast<float*>(smem + L::SM_QS);
   const float* sc_p = reinterpret_cast<const float*>(smem + L::SM_ROWS);
   const long long t0 = *reinterpret_cast<const long long*>(smem + L::SM_TILE0);
@@ -773,24 +802,29 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
   const P2 sc2(sc_hi, 0.f);
   // ---- epilogue (owners): G from TMEM, feature gradient, J_FK^T, records into shared memory ------------------------
   named_sync(TCB_EPI, QT);
-  float gx[DC_MAX_DOF], xl[DC_MAX_DOF];
+  float gx[FG], xl[FG];
 #pragma unroll
-  for (int i = 0; i < DC_MAX_DOF; ++i) {
+  for (int i = 0; i < FG; ++i) {
     gx[i] = 0.f;
-    xl[i] = xs[row * 16 + i];
+    xl[i] = xs[row * FG + i];
   }
-  mbar_wait_wd(&bar_g[ti & 1], (uint32_t)((ti >> 1) & 1));
+  // G accumulator(s): two of them alternate with the tile parity (FG 16), or one is reused by every tile (FG 32)
+  const int gb = (L::G_BUFS == 2) ? (ti & 1) : 0;
+  mbar_wait_wd(&bar_g[gb], (uint32_t)(((L::G_BUFS == 2) ? (ti >> 1) : ti) & 1));
   tc_fence_after();
   DC_TC_TRACE_TILE(4, 11);
   if constexpr (MODE == TC_GRAD) {
-    uint32_t gm[16], gc[16];
-    tmem_ld16(tm_lane + L::COL_G + (uint32_t)(ti & 1) * L::N2, gm);
-    tmem_ld16(tm_lane + L::COL_G + (uint32_t)(ti & 1) * L::N2 + 16, gc);
+    uint32_t gm[FG], gc[FG];  // columns [0, FG): sum cc w [s | 1] (hi terms); [FG, 2 FG): the low-part corrections
+#pragma unroll
+    for (int v = 0; v < FG / 16; ++v) {
+      tmem_ld16(tm_lane + L::COL_G + (uint32_t)gb * L::N2 + 16 * v, gm + 16 * v);
+      tmem_ld16(tm_lane + L::COL_G + (uint32_t)gb * L::N2 + FG + 16 * v, gc + 16 * v);
+    }
     tmem_wait_ld();
 #ifdef DC_TC_ENABLE_TRACE
     if (a.dbg != nullptr && t0 + ti == 0) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
+      for (int c = 0; c < 16; ++c) {  // (probe: FG 16 only)
         a.dbg[(size_t)TM * (nch * NC) + row * 32 + c] = __uint_as_float(gm[c]);
         a.dbg[(size_t)TM * (nch * NC) + row * 32 + 16 + c] = __uint_as_float(gc[c]);
       }
@@ -800,7 +834,7 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
 #pragma unroll
     for (int f = 0; f < FM; ++f) {
       const float gsum = __uint_as_float(gm[f]) + __uint_as_float(gc[f]);              // sum cc w s
-      const float gex = gacc_w[lane * 16 + f - 4 * 32 * 16] + gacc_w[lane * 16 + f];  // column halves 0 + 1
+      const float gex = gacc_w[lane * FG + f - 4 * 32 * FG] + gacc_w[lane * FG + f];  // column halves 0 + 1
       gx[f] = a.rc.grad_scale * (fmaf(xl[f], csum, -gsum) * inv_g + gex);
     }
   }
@@ -820,10 +854,10 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
         float gq[DC_MAX_DOF];
 #pragma unroll
         for (int i = 0; i < DC_MAX_DOF; ++i) gq[i] = 0.f;
-        if (a.fk.type == DC_FK_PLANAR_CHAIN) {
-          fk_planar_vjp_reg<FM / 2>(a.fk.n_links, xl, gx, gq);  // the BASELINE robot: J^T in registers
+        if (FG == 16 && a.fk.type == DC_FK_PLANAR_CHAIN && a.fk.n_repeat <= 1 && !a.fk.time_last) {
+          fk_planar_vjp_reg<7>(a.fk.n_links, xl, gx, gq);  // the BASELINE robot: J^T in registers
 #pragma unroll
-          for (int i = 0; i < FM / 2; ++i)
+          for (int i = 0; i < 7; ++i)
             if (i < a.n_in) rec[1 + i] = scale * gq[i];
         } else {
           float qv[DC_MAX_DOF];
@@ -890,9 +924,9 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
   DC_TC_TRACE_TILE(4, 13);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __grid_constant__ TcArgs a) {
-  using L = TcLayout;
+template <int MODE, int FG = 16>
+__global__ void __launch_bounds__(TcLayoutT<FG>::THREADS, TcLayoutT<FG>::CTAS_PER_SM) score_tc_kernel(const __grid_constant__ TcArgs a) {
+  using L = TcLayoutT<FG>;
   constexpr int NC = L::NC, QT = L::QTHREADS, TM = L::TM;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -912,7 +946,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
   unsigned char* ring2 = smem + L::SM_RING2;
   unsigned char* a_op = smem + L::SM_A;
   float* sacc = reinterpret_cast<float*>(smem + L::SM_ACC);      // [8][32]
-  float* gacc = sacc + L::QWARPS * 32;                           // [8][32][16]
+  float* gacc = sacc + L::QWARPS * 32;                           // [8][32][FG]
   float* sc_p = reinterpret_cast<float*>(smem + L::SM_ROWS);     // [128] score partial of the lower column half
   const float2* thr_all = reinterpret_cast<const float2*>(sc_p + TM);  // [2][128] near-threshold line (c0, c1) of each query
   uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L::SM_QUEUE);
@@ -954,7 +988,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
     __syncwarp();
     tmem_alloc(tmem_slot, L::TMEM_COLS);
   } else if (warp == 0 && lane < 12) {
-    reinterpret_cast<float*>(smem + L::SM_TRAILER)[lane] = tc_trailer(a.blob, a.n_sv)[lane];
+    reinterpret_cast<float*>(smem + L::SM_TRAILER)[lane] = tc_trailer(a.blob, a.n_sv, FG)[lane];
   } else if (warp == 1 && lane == 0) {
     *reinterpret_cast<long long*>(smem + L::SM_TILE0) = t0;
   }
@@ -1005,7 +1039,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
             if constexpr (MODE == TC_GRAD) {
               const uint32_t b_s = smem_u32(ring2 + (size_t)st * L::B2W_BYTES);
               const uint32_t cc = tmem + st * L::COL_STAGE;
-              const uint32_t d = tmem + L::COL_G + (uint32_t)(ti & 1) * L::N2;
+              const uint32_t d = tmem + L::COL_G + (uint32_t)((L::G_BUFS == 2) ? (ti & 1) : 0) * L::N2;
 #pragma unroll
               for (int ks = 0; ks < L::KS2; ++ks) {
                 const uint64_t bd = umma_desc(b_s + ks * L::B2_STEP_BYTES, L::N2 * 16, 128);
@@ -1013,7 +1047,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
               }
             }
             umma_commit(&bar_b2free[st]);
-            if (j == nch - 1) umma_commit(&bar_g[ti & 1]);
+            if (j == nch - 1) umma_commit(&bar_g[(L::G_BUFS == 2) ? (ti & 1) : 0]);
           }
           __syncwarp();
           DC_TC_TRACE(4, g);
@@ -1078,14 +1112,14 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
     const bool owner = hcol == 1;
     const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t* queue = queues + warp * L::QCAP;
-    float* gacc_w = gacc + warp * 32 * 16;
+    float* gacc_w = gacc + warp * 32 * FG;
     float* sacc_w = sacc + warp * 32;
 #ifdef DC_TC_ENABLE_TRACE
-    const float* trailer = tc_trailer(a.blob, a.n_sv);
+    const float* trailer = tc_trailer(a.blob, a.n_sv, FG);
     const float tau = trailer[5], inv_tc0 = trailer[9];
 #endif
 
-    if (!owner && ntile > 0) tc_fk_stage(a, 0, tid);
+    if (!owner && ntile > 0) tc_fk_stage<FG>(a, 0, tid);
 
     uint32_t g = 0;
     for (int ti = 0; ti < ntile; ++ti) {
@@ -1098,8 +1132,9 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
       DC_TC_TRACE_TILE(0, 0);
       DC_TC_TRACE_TILE(4, 8);
       {
-        float4* z = reinterpret_cast<float4*>(gacc_w + lane * 16);
-        z[0] = z[1] = z[2] = z[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* z = reinterpret_cast<float4*>(gacc_w + lane * FG);
+#pragma unroll
+        for (int v = 0; v < FG / 4; ++v) z[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         sacc_w[lane] = 0.f;
       }
       __syncwarp();
@@ -1174,7 +1209,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
               qcount += __popc(bal);
               if (qcount > L::QCAP - 32) {
                 __syncwarp();
-                tc_drain_pairs(a, qcount, warp, buf);
+                tc_drain_pairs<FG>(a, qcount, warp, buf);
                 __syncwarp();
                 qcount = 0;
               }
@@ -1246,7 +1281,7 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
       DC_TC_TRACE_TILE(4, 9);
       if (qcount > 0) {
         __syncwarp();
-        tc_drain_pairs(a, qcount, warp, buf);
+        tc_drain_pairs<FG>(a, qcount, warp, buf);
       }
       DC_TC_TRACE_TILE(0, 2);
       DC_TC_TRACE_TILE(4, 10);
@@ -1256,12 +1291,12 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
         // bar.arrive orders this thread's prior shared-memory writes for the threads that complete the barrier; a
         // sequentially consistent fence here (MEMBAR.SC) cost ~2000 cycles per tile on the path to the next tile's FK
         named_arrive(TCB_EPI, QT);  // lower half's partial scores and exact terms of tile ti are complete
-        if (ti + 1 < ntile) tc_fk_stage(a, ti + 1, tid);
+        if (ti + 1 < ntile) tc_fk_stage<FG>(a, ti + 1, tid);
         DC_TC_TRACE_TILE(0, 3);
         continue;
       }
 
-      tc_epilogue<MODE>(a, ti, ntile, sc2.lo() + sc2.hi());
+      tc_epilogue<MODE, FG>(a, ti, ntile, sc2.lo() + sc2.hi());
     }
     if (tid == TM && a.n_bcast > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // peer stores performed
   }
@@ -1288,25 +1323,29 @@ __global__ void __launch_bounds__(TcLayout::THREADS, 2) score_tc_kernel(const __
 inline int launch_pack_supports_tc(const float* s_feat, const float* w, long long n, int F, float gamma, unsigned char* blob,
                                    cudaStream_t stream) {
   using L = TcLayout;
-  const int nch = tc_n_chunks(n);
-  DC_CUDA_OK(cudaMemsetAsync(blob, 0, tc_blob_bytes(n), stream));
-  int* trailer = reinterpret_cast<int*>(const_cast<float*>(tc_trailer(blob, n)));
+  const int nch = tc_n_chunks(n), fg = tc_group(F);
+  DC_CUDA_OK(cudaMemsetAsync(blob, 0, tc_blob_bytes(n, fg), stream));
+  int* trailer = reinterpret_cast<int*>(const_cast<float*>(tc_trailer(blob, n, fg)));
   tc_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(s_feat, w, (int)n, F, trailer);
   DC_LAUNCH_CHECK();
-  pack_supports_tc_kernel<<<(unsigned)((nch * L::NC + 127) / 128), 128, 0, stream>>>(s_feat, w, (int)n, F, nch, gamma, blob);
+  const unsigned grid = (unsigned)((nch * L::NC + 127) / 128);
+  if (fg == 16)
+    pack_supports_tc_kernel<16><<<grid, 128, 0, stream>>>(s_feat, w, (int)n, F, nch, gamma, blob);
+  else
+    pack_supports_tc_kernel<32><<<grid, 128, 0, stream>>>(s_feat, w, (int)n, F, nch, gamma, blob);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }
 
-template <int MODE>
-int launch_score_tc(TcArgs& a, int num_sms, cudaStream_t stream) {
-  using L = TcLayout;
+template <int MODE, int FG>
+int launch_score_tc_fg(TcArgs& a, int num_sms, cudaStream_t stream) {
+  using L = TcLayoutT<FG>;
   a.n_tiles = (int)ceil_div64(a.batch, L::TM);
   a.n_chunks = tc_n_chunks(a.n_sv);
-  const int grid = (int)min((long long)2 * num_sms, (long long)a.n_tiles);
+  const int grid = (int)min((long long)L::CTAS_PER_SM * num_sms, (long long)a.n_tiles);
   if (((long long)a.n_tiles / grid + 1) * a.n_chunks >= (1LL << 31) || a.n_sv >= (1 << 24)) return DC_ERR_UNSUPPORTED;
-  if (a.fk.type != DC_FK_NONE && a.n_in > L::QS_DOF) return DC_ERR_UNSUPPORTED;
-  auto kern = score_tc_kernel<MODE>;
+  if (a.n_feat > L::FMAX || (a.fk.type != DC_FK_NONE && a.n_in > L::QS_DOF)) return DC_ERR_UNSUPPORTED;
+  auto kern = score_tc_kernel<MODE, FG>;
   {
     static PerDeviceOnce once;
     int dev = 0;
@@ -1321,6 +1360,13 @@ int launch_score_tc(TcArgs& a, int num_sms, cudaStream_t stream) {
   kern<<<grid, L::THREADS, L::SM_BYTES, stream>>>(a);
   DC_LAUNCH_CHECK();
   return DC_OK;
+}
+
+// F <= 14: operand groups of 16 K slots, two CTAs per SM (the BASELINE shape); F <= 30: groups of 32, one CTA per SM.
+template <int MODE>
+int launch_score_tc(TcArgs& a, int num_sms, cudaStream_t stream) {
+  return tc_group(a.n_feat) == 16 ? launch_score_tc_fg<MODE, 16>(a, num_sms, stream)
+                                  : launch_score_tc_fg<MODE, 32>(a, num_sms, stream);
 }
 
 }  // namespace dc

@@ -55,13 +55,14 @@ struct ScoreArgs {
   int chunk_rows;
 };
 
-// NWG = warps per group (4 or 16).  A CTA always has 16 warps = 16/NWG groups; a group owns one 64-query tile at a time
+// NWG = warps per group (4 or NW).  A CTA has NW = 16 warps (8 for F > 16: the per-lane state of 3F packed registers then
+// needs the 255 registers a 256-thread CTA leaves per thread) = NW/NWG groups; a group owns one 64-query tile at a time
 // and its NWG warps split the support set.  NWG = 4 (four concurrent tiles per SM, group-local named barriers, 4-way
 // reduction) is the throughput configuration; NWG = 16 (one tile per SM at a time) keeps every warp busy when the
 // batch has fewer than ~4 tiles per SM.
 template <int F, int CW, int MODE, int NWG, int STAGES>
 struct TqCfg {
-  static constexpr int NW = 16;
+  static constexpr int NW = F > 16 ? 8 : 16;
   static constexpr int NGRP = NW / NWG;
   static constexpr int GT = NWG * 32;  // threads per group
   static constexpr int FPAD = round_up(F, 2);
@@ -84,7 +85,7 @@ __device__ __forceinline__ void group_barrier(int id, int threads) {
 }
 
 template <int F, int KIND, int CW, int MODE, int NWG, int STAGES>
-__global__ void __launch_bounds__(512, 1) score_tq_kernel(const __grid_constant__ ScoreArgs<float> a) {
+__global__ void __launch_bounds__(TqCfg<F, CW, MODE, NWG, STAGES>::NW * 32, 1) score_tq_kernel(const __grid_constant__ ScoreArgs<float> a) {
   using T = float;
   using Cfg = TqCfg<F, CW, MODE, NWG, STAGES>;
   constexpr int NW = Cfg::NW, NGRP = Cfg::NGRP, GT = Cfg::GT;
@@ -367,7 +368,7 @@ int launch_score_tq(ScoreArgs<float>& a, int num_sms, cudaStream_t stream) {
   auto kern = score_tq_kernel<F, KIND, CW, MODE, NWG, STAGES>;
   DC_SET_FUNC_ATTR_ONCE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);  // per instantiation, per device
   const int grid = (int)min((long long)num_sms, (long long)ceil_div64(a.n_tiles, Cfg::NGRP));
-  kern<<<grid, 512, smem, stream>>>(a);
+  kern<<<grid, Cfg::NW * 32, smem, stream>>>(a);
   DC_LAUNCH_CHECK();
   return DC_OK;
 }

@@ -81,7 +81,7 @@ class SupportSet:
                                             self.table.data_ptr(), _stream_ptr(device)), "dc_pack_supports")
         self.dtype = dtype
         self.device = device
-        # Optional tensor-core operand image (fp32, one class, F <= 14, RQKernel with p = 2; csrc/dc_score_tc.cuh): the
+        # Optional tensor-core operand image (fp32, one class, F <= 30, RQKernel with p = 2; csrc/dc_score_tc.cuh): the
         # kernel width and the weights are folded into the operands, so it is built for the kernel this support set is
         # scored with.  max|s|^2 and the range check are read back once here (pack time).
         self.tc_blob = None
@@ -96,7 +96,7 @@ class SupportSet:
                 _lib.check(lib.dc_pack_supports_tc(s.data_ptr(), w.data_ptr(), self.n, self.n_features, C.byref(kernel), ptr,
                                                    _stream_ptr(device)), "dc_pack_supports_tc")
                 torch.cuda.current_stream(device).synchronize()
-                _lib.check(lib.dc_supports_tc_info(ptr, self.n, C.byref(s2), C.byref(valid)), "dc_supports_tc_info")
+                _lib.check(lib.dc_supports_tc_info(ptr, self.n, self.n_features, C.byref(s2), C.byref(valid)), "dc_supports_tc_info")
             if valid.value:
                 self.tc_blob, tc_ptr, s2max, tc_gamma = blob, ptr, s2.value, float(kernel.param)
         # Optional low parts of the features (fk_forward_split): what float32 rounding dropped from FK(support) — the

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 5
+#define DC_ABI_VERSION 6
 
 #define DC_MAX_DOF 16
 #define DC_MAX_LINKS 16
@@ -179,7 +179,8 @@ int dc_pack_supports(const void* s_feat, const void* w, int64_t n, int32_t n_fea
                      void* table, dc_stream_t stream);
 
 /*
- * Tensor-core operand image of a support set (fp32, one class, n_features <= 14, RQKernel with p = 2):
+ * Tensor-core operand image of a support set (fp32, one class, n_features <= 30, RQKernel with p = 2; the layout
+ * depends on whether n_features <= 14, so every call names n_features):
  * dc_supports_tc_bytes gives the buffer size (DC_ERR_UNSUPPORTED for shapes the tensor-core kernel does not cover),
  * dc_pack_supports_tc fills a 128-byte aligned device buffer from S_feat[N,F], W[N] and the kernel (gamma and the
  * weights are folded into the operands, so the image belongs to this (S, W, kernel) triple).  dc_supports_tc_info
@@ -189,7 +190,7 @@ int dc_pack_supports(const void* s_feat, const void* w, int64_t n, int32_t n_fea
 int dc_supports_tc_bytes(int64_t n, int32_t n_features, int32_t n_class, int32_t dtype, int64_t* bytes);
 int dc_pack_supports_tc(const void* s_feat, const void* w, int64_t n, int32_t n_features, const dc_kernel_desc* kernel,
                         void* blob, dc_stream_t stream);
-int dc_supports_tc_info(const void* blob, int64_t n, double* s2max, int32_t* valid);
+int dc_supports_tc_info(const void* blob, int64_t n, int32_t n_features, double* s2max, int32_t* valid);
 
 /* Process-wide tuning knobs (the only global state of the library besides the launch counter). */
 typedef enum dc_option {

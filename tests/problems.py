@@ -61,6 +61,8 @@ def make_robot(name):
         return M.RevolutePlanarRobot([1.0, 0.8, 0.6], 0.3)
     if name == "planar7":
         return M.RevolutePlanarRobot(1.0, 0.3, dof=7)
+    if name == "planar15":  # F = 30: the widest map the tensor-core image holds
+        return M.RevolutePlanarRobot(0.5, 0.1, dof=15)
     if name == "se2":
         return M.RigidPlanarBody([("box", (0.5, 0.2), (1, 1)), ("box", (-0.4, 0.3), (1, 1)), ("box", (0.1, -0.6), (1, 1)),
                                   ("box", (-0.3, -0.2), (1, 1)), ("box", (0.7, 0.7), (1, 1))])

@@ -14,7 +14,7 @@ from tests.test_gpu_parity import cuda_support_set, kernel_pair, oracle_score_gr
 
 pytestmark = pytest.mark.gpu
 
-TC, TQ = 2, 1
+TC, TQ, LS = 2, 1, 0
 
 
 @pytest.fixture(scope="module")
@@ -86,6 +86,51 @@ def test_tensor_core_kernel_matches_oracle_and_fp32_kernel(rname, dev, lib):
     _, g_ref2 = oracle_score_grad(robot, kspec, S, W, q, go)
     _, g2, _ = run(lib, robot, kfun, sv, qd, _lib.DC_GRAD_SUM, tc=True, go=go.to(device=dev, dtype=torch.float32))
     assert rel(g2, g_ref2) <= gate
+
+
+@pytest.mark.parametrize("gamma,forced", [(10.0, True), (300.0, False)])
+@pytest.mark.parametrize("rname", ["panda", "baxter_dual", "planar15"])
+def test_wide_feature_maps_on_the_tensor_core_kernel(rname, gamma, forced, dev, lib):
+    """15 <= F <= 30 (Panda 21, dual Baxter 24, a 15-link planar arm 30): operand groups of 32 K slots, one CTA per SM.  With the
+    reference's default width (gamma = 10) these metre-scale maps are wider than the kernel — a large share of the pairs
+    is "near" and the dispatcher rightly keeps the FP32-pipe kernels; the tensor-core instantiation is then forced
+    (max|s|^2 declared unknown) to hold ITS arithmetic to the same 1e-5.  With a narrow kernel it is chosen on its own."""
+    from diffco_b200 import _lib
+    from diffco_b200 import kernel as K
+    from oracle import diffco_oracle as O
+
+    robot, S, W = P.synthetic_model(rname, 1501, 1, seed=410)
+    gen = torch.Generator().manual_seed(411)
+    q = P.sample_configs(robot, 8192 + 77, gen)
+    q[10] = S[3]
+    q[4000:4200] = S[:200] + 0.05 * torch.randn(200, robot.dof, generator=gen, dtype=torch.float64)
+    q[6000:6400] = S[200:600] + 0.2 * torch.randn(400, robot.dof, generator=gen, dtype=torch.float64)
+    q = q.float().double()
+    S, W = S.float().double(), W.float().double()
+    kfun, kspec = K.RQKernel(gamma), O.KernelSpec("rq", gamma, 2)
+    s_ref, g_ref = oracle_score_grad(robot, kspec, S, W, q)
+    sv = cuda_support_set(robot, S, W, torch.float32, dev, kfun=kfun)
+    assert sv.tc_blob is not None and sv.n_features > 14
+    if forced:
+        sv.desc.tc_s2max = 0.0
+    qd = q.to(device=dev, dtype=torch.float32)
+    assert lib.dc_set_option(_lib.DC_OPT_TC_STATS, 1.0) == 0
+    s, g, which = run(lib, robot, kfun, sv, qd, _lib.DC_GRAD_SUM, tc=True)
+    near = lib.dc_get_option(_lib.DC_OPT_TC_STATS) / (len(q) * len(S))
+    assert lib.dc_set_option(_lib.DC_OPT_TC_STATS, 0.0) == 0
+    assert which == TC, _lib.KERNEL_NAMES[which]
+    s0, g0, which0 = run(lib, robot, kfun, sv, qd, _lib.DC_GRAD_SUM, tc=False)
+    assert which0 == (TQ if sv.n_features in (21, 24, 27) else LS)  # thread-per-query instantiations: F <= 16, 21, 24, 27
+    es, eg, es0, eg0 = rel(s, s_ref), rel(g, g_ref), rel(s0, s_ref), rel(g0, g_ref)
+    print(f"{rname} gamma {gamma}: F = {sv.n_features}, exact-path pairs {100 * near:.2f} % | tensor-core score {es:.2e} grad {eg:.2e} "
+          f"| lane-split score {es0:.2e} grad {eg0:.2e}", flush=True)
+    assert es <= 1e-5 and eg <= 1e-5
+    s1, none, _ = run(lib, robot, kfun, sv, qd, _lib.DC_GRAD_NONE, tc=True)
+    assert none is None and rel(s1, s_ref) <= 1e-5
+    # position independence: the same rows in another order give the same bits
+    perm = torch.randperm(len(q), generator=gen)
+    sp, gp, _ = run(lib, robot, kfun, sv, qd[perm.to(dev)], _lib.DC_GRAD_SUM, tc=True)
+    assert torch.equal(sp, s[perm.to(dev)]) and torch.equal(gp, g[perm.to(dev)])
 
 
 def test_cfg2_full_size_sampled_rows_and_position_independence(dev, lib):
@@ -188,11 +233,11 @@ def test_dispatch_rules(dev, lib):
     assert run(lib, robot, K.Polyharmonic(1, 1.0), sv, q, _lib.DC_GRAD_SUM, tc=True)[2] == TQ
     assert run(lib, robot, rq, sv, q, _lib.DC_GRAD_JAC, tc=True)[2] != TC or sv.n_class == 1
     assert lib.dc_set_option(99, 1.0) != 0 and lib.dc_set_option(2, -1.0) != 0
-    # multi-class and wide feature maps have no tensor-core image
+    # multi-class models have no tensor-core image; feature maps up to F = 30 do (Panda: F = 21)
     robot2, S2, W2 = P.synthetic_model("baxter", 200, 4, seed=342)
     assert cuda_support_set(robot2, S2, W2, torch.float32, dev).tc_blob is None
     robot3, S3, W3 = P.synthetic_model("panda", 200, 1, seed=343)
-    assert cuda_support_set(robot3, S3, W3, torch.float32, dev).tc_blob is None
+    assert cuda_support_set(robot3, S3, W3, torch.float32, dev).tc_blob is not None
 
 
 @pytest.mark.parametrize("n_sv", [50, 96, 97, 193])

@@ -92,7 +92,9 @@ def test_tensor_core_peer_and_trajectory_entry_points_validate_arguments(lib):
     assert lib.dc_supports_tc_bytes(2000, 14, 1, _lib.DC_F32, C.byref(n)) == 0
     # 21 chunks of 96 supports: GEMM1 image, GEMM2 image + fp32 weights + chunk maximum, trailer
     assert n.value == 21 * (9216 + 12800) + 64
-    assert lib.dc_supports_tc_bytes(2000, 15, 1, _lib.DC_F32, C.byref(n)) == -2   # F > 14
+    assert lib.dc_supports_tc_bytes(2000, 15, 1, _lib.DC_F32, C.byref(n)) == 0    # 15 <= F <= 30: operand groups of 32 K slots
+    assert n.value == 21 * (96 * 96 * 2 + 12 * 2048 + 512) + 64
+    assert lib.dc_supports_tc_bytes(2000, 31, 1, _lib.DC_F32, C.byref(n)) == -2   # F > 30
     assert lib.dc_supports_tc_bytes(2000, 14, 4, _lib.DC_F32, C.byref(n)) == -2   # multi-class
     assert lib.dc_supports_tc_bytes(2000, 14, 1, _lib.DC_F64, C.byref(n)) == -2   # float64
     assert lib.dc_supports_tc_bytes(0, 14, 1, _lib.DC_F32, C.byref(n)) == -1
@@ -102,7 +104,7 @@ def test_tensor_core_peer_and_trajectory_entry_points_validate_arguments(lib):
     assert lib.dc_pack_supports_tc(64, 64, 10, 14, None, 128, None) == -1         # the image is built for one kernel
     ph = _lib.KernelDesc(_lib.DC_K_POLYHARMONIC, 1, 1.0)
     assert lib.dc_pack_supports_tc(64, 64, 10, 14, C.byref(ph), 128, None) == -2  # RQKernel(p = 2) only
-    assert lib.dc_supports_tc_info(None, 10, None, None) == -1
+    assert lib.dc_supports_tc_info(None, 10, 14, None, None) == -1
     saved = [lib.dc_get_option(k) for k in (1, 2, 3, 4)]
     try:
         assert lib.dc_set_option(_lib.DC_OPT_TC_ERR_COEF, 1e-6) == 0 and lib.dc_get_option(_lib.DC_OPT_TC_ERR_COEF) == 1e-6
