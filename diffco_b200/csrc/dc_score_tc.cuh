@@ -50,6 +50,12 @@
 #ifndef DC_TC_FK_UNROLL
 #define DC_TC_FK_UNROLL 1  // joints per iteration of the planar FK loop of the tile prologue (code size vs. latency overlap)
 #endif
+#ifndef DC_TC_HANDOVER
+#define DC_TC_HANDOVER 0  // 1: the lower half leaves its end-of-tile queue drain to the owner warps and goes straight to the
+#endif                    //    next tile's FK: the CTA's tile-to-tile gap shrinks from 20 k to 13 k cycles, the kernel does not
+                          //    get faster (90.0 vs 89.5 us, 2.26 vs 2.23 ms at 2 M queries) — with two CTAs per SM one CTA's gap
+                          //    is the other's chance to run its chunk loop alone; SM-level throughput is what binds
+                          //    (profiles/r03e_handover.txt)
 #ifndef DC_TC_DEPHASE
 #define DC_TC_DEPHASE 0   // 1: the owner half starts each tile half a chunk behind the lower half: 93.6 us vs 92.9 us
 #endif
@@ -105,6 +111,7 @@ struct TcLayoutT {
   static constexpr int SM_TILE0 = 184;      // first tile of this CTA (long long): the out-of-line stages read it back
                                             // instead of redoing the 64-bit division (cold code on the tile-to-tile path)
   static constexpr int SM_TMEM_SLOT = 192;
+  static constexpr int SM_QHAND = 208;      // int[4]: queue entries each lower-half warp leaves to its owner warp
   static constexpr int SM_RING1 = 256;
   static constexpr int SM_RING2 = SM_RING1 + RS1 * B1_BYTES;
   static constexpr int SM_A = SM_RING2 + RS2 * B2W_BYTES;   // A [K1/8][128][8] f16
@@ -802,6 +809,14 @@ __device__ __noinline__ void tc_epilogue(const TcArgs& a, int ti, int ntile, flo
   const P2 sc2(sc_hi, 0.f);
   // ---- epilogue (owners): G from TMEM, feature gradient, J_FK^T, records into shared memory ------------------------
   named_sync(TCB_EPI, QT);
+  {
+    // entries the lower-half warp of this lane quarter handed over (tiles with a successor): applied to ITS accumulators
+    const int handed = reinterpret_cast<const int*>(smem + L::SM_QHAND)[warp - 4];
+    if (handed > 0) {
+      tc_drain_pairs<FG>(a, handed, warp - 4, buf);
+      __syncwarp();
+    }
+  }
   float gx[FG], xl[FG];
 #pragma unroll
   for (int i = 0; i < FG; ++i) {
@@ -1279,7 +1294,11 @@ __global__ void __launch_bounds__(TcLayoutT<FG>::THREADS, TcLayoutT<FG>::CTAS_PE
       }
       DC_TC_TRACE_TILE(0, 1);
       DC_TC_TRACE_TILE(4, 9);
-      if (qcount > 0) {
+      // (DC_TC_HANDOVER, measured, off: with another tile to come the lower half hands what is left in its queue to the
+      // owner warp of the same TMEM lane quarter and goes straight to the FK stage; that warp applies the entries to the
+      // LOWER warp's accumulators, in queue order, before it reads them — same additions, same order, same bits.)
+      const bool hand_over = DC_TC_HANDOVER && !owner && (ti + 1 < ntile);
+      if (qcount > 0 && !hand_over) {
         __syncwarp();
         tc_drain_pairs<FG>(a, qcount, warp, buf);
       }
@@ -1287,6 +1306,7 @@ __global__ void __launch_bounds__(TcLayoutT<FG>::THREADS, TcLayoutT<FG>::CTAS_PE
       DC_TC_TRACE_TILE(4, 10);
 
       if (!owner) {
+        if (lane == 0) reinterpret_cast<int*>(smem + L::SM_QHAND)[warp] = hand_over ? qcount : 0;
         sc_p[row] = sc2.lo() + sc2.hi();
         // bar.arrive orders this thread's prior shared-memory writes for the threads that complete the barrier; a
         // sequentially consistent fence here (MEMBAR.SC) cost ~2000 cycles per tile on the path to the next tile's FK
