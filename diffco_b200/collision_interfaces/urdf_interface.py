@@ -111,7 +111,7 @@ class URDFRobot(Model):
     origins of the link frames whose joint has a non-zero translation, (B, L, 3) — is fused into the score kernels through
     ``fk_desc``; the reference stacks the same points as (B, 3, L) (``tensorized_fkine``), which is the same feature set."""
 
-    def __init__(self, urdf_path, name="", base_transform: Optional[torch.Tensor] = None, device="cuda", setup_acm=False,
+    def __init__(self, urdf_path, name="", base_transform: Optional[torch.Tensor] = None, device="cpu", setup_acm=False,
                  load_visual_meshes=False):
         if load_visual_meshes:
             raise NotImplementedError("meshes (trimesh) are outside this package")

@@ -91,3 +91,16 @@ def test_peer_exchange_setup_fails_consistently_without_peer_memory():
     results = mp.get_context("spawn").Manager().dict()
     mp.spawn(_peer_failure_worker, args=(world, _free_port(), results), nprocs=world, join=True)
     assert all(results.get(r) for r in range(world)), dict(results)
+
+
+def test_numa_binding_helper_leaves_the_process_alone_without_a_gpu():
+    """bind_host_thread_to_gpu pins a rank to its GPU's NUMA-local CPUs before it allocates pinned buffers; when the
+    topology cannot be read (no NVML / no GPU, as here) it must return None and change nothing."""
+    import os
+
+    from diffco_b200 import distributed as D
+
+    before = os.sched_getaffinity(0)
+    assert D.bind_host_thread_to_gpu(0) is None or os.sched_getaffinity(0) <= before
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
