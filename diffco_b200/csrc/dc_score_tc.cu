@@ -78,7 +78,7 @@ bool takes_tensor_core_kernel(const dc_fk_desc& fk, const dc_kernel_desc& kernel
                               int grad_mode) {
   if (!tc_enabled() || sv.tc_blob == nullptr) return false;
   const int F = fk.type == DC_FK_NONE ? fk.dof : fk.n_points * fk.point_dim;
-  if (!tc_shape_ok(F, sv.n_class, sv.dtype) || fk.dof > DC_MAX_DOF) return false;
+  if (!tc_shape_ok(F, sv.n_class, sv.dtype) || (fk.type != DC_FK_NONE && fk.dof > DC_MAX_DOF)) return false;  // NONE: dof == F
   if (fk.n_repeat > 1 || fk.time_last) return false;  // composite maps (line / temporal kernels): lane-split or thread-per-query
   if (kernel.kind != DC_K_RQ || kernel.order != 2 || !(kernel.param > 0)) return false;
   if ((float)kernel.param != (float)sv.tc_gamma) return false;  // the operand image has the kernel width folded in

@@ -129,6 +129,7 @@ struct TcLayoutT {
   static_assert(CTAS_PER_SM * (SM_BYTES + 1024) <= 233472, "the CTAs of one SM must fit in 228 KB of shared memory");
   static_assert(SM_BYTES <= 232448, "at most 227 KB of dynamic shared memory per CTA");
   static_assert(TM * (DC_MAX_DOF + 1) * 4 <= 4 * 32 * FG * 4 + 512, "output records must fit the owners' accumulators");
+  static_assert(TM * (FMAX + 1) * 4 <= 4 * 32 * FG * 4 + 512, "... also for transform=None, where a record is [score | d/dx (F)]");
 };
 using TcLayout = TcLayoutT<16>;
 __host__ __device__ constexpr int tc_group(int n_features) { return n_features <= 14 ? 16 : 32; }

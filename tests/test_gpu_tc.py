@@ -133,6 +133,33 @@ def test_wide_feature_maps_on_the_tensor_core_kernel(rname, gamma, forced, dev, 
     assert torch.equal(sp, s[perm.to(dev)]) and torch.equal(gp, g[perm.to(dev)])
 
 
+@pytest.mark.parametrize("n_feat", [9, 14, 15, 22, 30])
+def test_raw_feature_rows_on_the_tensor_core_kernel(n_feat, dev, lib):
+    """transform=None (kernel_perceptrons.py:36; poly_score(transformed_point=...) :316-317): the rows ARE the features and
+    gradients are w.r.t. them — both instantiations (F <= 14 and 15 <= F <= 30), records of up to 31 floats per query."""
+    from diffco_b200 import _lib
+    from diffco_b200 import functional as Fn
+    from diffco_b200 import kernel as K
+
+    gen = torch.Generator().manual_seed(500 + n_feat)
+    S = (torch.randn(1203, n_feat, generator=gen, dtype=torch.float64) * 1.5).float().double()
+    W = torch.randn(1203, 1, generator=gen, dtype=torch.float64).float().double()
+    q = torch.randn(8192 + 31, n_feat, generator=gen, dtype=torch.float64) * 1.5
+    q[100:300] = S[:200] + 0.02 * torch.randn(200, n_feat, generator=gen, dtype=torch.float64)
+    q = q.float().double()
+    kfun, kspec = K.RQKernel(6.0), O.KernelSpec("rq", 6.0, 2)
+    f = lambda z: O.score_original(z, None, kspec, S, W)
+    s_ref, g_ref = O.score_and_grad(f, q)
+    sv = Fn.SupportSet(S.float().to(dev), W.float().to(dev), dev, kernel=kfun.desc)
+    assert sv.tc_blob is not None
+    sv.desc.tc_s2max = 0.0  # "unknown": skip the dispatcher's width test, this case is about the transform=None path
+    fk = Fn.none_fk(n_feat)
+    assert lib.dc_set_option(1, 1.0) == 0
+    s, g = Fn.score_grad(fk, kfun.desc, sv, q.float().to(dev), _lib.DC_GRAD_SUM)
+    assert lib.dc_last_score_kernel() == TC
+    assert rel(s, s_ref.reshape(len(q), -1)) <= 1e-5 and rel(g, g_ref) <= 1e-5
+
+
 def test_cfg2_full_size_sampled_rows_and_position_independence(dev, lib):
     """BASELINE.json configs[1] (7-DoF planar arm, 2000 SVs, batch 65536) on the tensor-core kernel: 512 sampled rows
     against the oracle, and bit-identical rows when the batch is permuted (a row's result may not depend on its tile)."""
