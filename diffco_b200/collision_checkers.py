@@ -52,10 +52,14 @@ class CollisionChecker:
         if robot_topic is not None or planning_scene_topic is not None:
             raise NotImplementedError("ROS / MoveIt robots are outside this package: pass a URDF path, a URDFRobot or a "
                                       "diffco_b200.model robot")
-        if isinstance(robot, str):  # collision_checkers.py:52-56: a path to a URDF file
+        if isinstance(robot, str):  # collision_checkers.py:49-59: a path to a URDF file
+            import os
+
             from .collision_interfaces import URDFRobot
 
-            robot = URDFRobot(robot, base_transform=robot_base_transform, device=device)
+            if not os.path.isfile(robot):
+                raise ValueError("Invalid robot URDF file path")
+            robot = URDFRobot(robot, name=os.path.basename(robot).split(".")[0], base_transform=robot_base_transform, device=device)
         if robot is None or not hasattr(robot, "fkine") or not hasattr(robot, "limits"):
             raise TypeError("robot must be a URDF path, a URDFRobot or a diffco_b200.model robot (dof, limits, fkine)")
         if gt_check_func is None:

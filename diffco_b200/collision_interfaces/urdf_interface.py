@@ -262,3 +262,84 @@ class URDFRobot(Model):
                 poses.append((trans[:, n] + rot[:, n] @ to, rot[:, n] @ ro))
             out[name] = poses
         return out
+
+
+class MultiURDFRobot(Model):
+    """urdf_interface.py:700-870: several URDF robots side by side.  Configurations are the robots' configurations
+    concatenated (``split_configs``); the feature map of ``ForwardKinematicsDiffCo`` is the concatenation of the robots'
+    feature links in robot order (collision_checkers.py:347-351,374-384).  The joint programs are merged into ONE
+    ``dc_fk_desc`` (node, column and output-slot indices shifted), so the combined map is fused into the score kernels like
+    a single robot — within the limits of the descriptor (24 bodies, 16 joints, 21 feature links in total)."""
+
+    def __init__(self, urdf_robots: Optional[List[URDFRobot]] = None, urdf_paths: Optional[List[str]] = None,
+                 names: Optional[List[str]] = None, base_transforms: Optional[List[torch.Tensor]] = None, name: str = None,
+                 device="cpu", setup_acm=False, load_visual_meshes=False):
+        if urdf_robots is not None:
+            self.urdf_robots = list(urdf_robots)
+            if len({r.name for r in self.urdf_robots}) != len(self.urdf_robots):
+                raise AssertionError("Robot names must be unique")
+            self.name = "_".join(r.name for r in self.urdf_robots) if name is None else name
+            self._device = self.urdf_robots[0]._device
+        else:
+            base_transforms = base_transforms if base_transforms is not None else [None] * len(urdf_paths)
+            self.urdf_robots = [URDFRobot(p, name=n, base_transform=b, device=device, setup_acm=setup_acm,
+                                          load_visual_meshes=load_visual_meshes)
+                                for p, n, b in zip(urdf_paths, names, base_transforms)]
+            self.name = "_".join(names) if name is None else name
+            self._device = torch.device(device)
+        self.inter_robot_acm = None
+        self._bodies = [list(r._bodies) for r in self.urdf_robots]
+        self._n_dofs = sum(r._n_dofs for r in self.urdf_robots)
+        self.dof = self._n_dofs
+        self.joint_limits = torch.cat([r.joint_limits for r in self.urdf_robots], dim=0)
+        self.limits = self.joint_limits
+        self.unique_position_link_names = [(i, n) for i, r in enumerate(self.urdf_robots) for n in r.unique_position_link_names]
+        self._merge()
+        self._finalize()
+
+    def _merge(self):
+        n_nodes = sum(r.fk_desc.n_nodes for r in self.urdf_robots)
+        n_slots = sum(r.fk_desc.n_points for r in self.urdf_robots)
+        if n_nodes > _lib.DC_MAX_TREE_NODES or self._n_dofs > _lib.DC_MAX_DOF or 3 * n_slots > _lib.DC_MAX_FEATURES:
+            raise ValueError(f"{n_nodes} bodies / {self._n_dofs} joints / {n_slots} feature links in total; the joint program holds "
+                             f"{_lib.DC_MAX_TREE_NODES} / {_lib.DC_MAX_DOF} / {_lib.DC_MAX_FEATURES // 3}")
+        d = _lib.FkDesc()
+        d.type = _lib.DC_FK_JOINT_TREE
+        d.dof, d.n_points, d.point_dim, d.n_nodes = self._n_dofs, n_slots, 3, n_nodes
+        node0 = col0 = slot0 = 0
+        self.node_names = []
+        for i, r in enumerate(self.urdf_robots):
+            src = r.fk_desc
+            for k in range(src.n_nodes):
+                nd = _lib.TreeNode.from_buffer_copy(src.tree[k])
+                if nd.parent >= 0:
+                    nd.parent += node0
+                if nd.q_index >= 0:
+                    nd.q_index += col0
+                if nd.out_slot >= 0:
+                    nd.out_slot += slot0
+                d.tree[node0 + k] = nd
+                self.node_names.append((i, r.node_names[k]))
+            node0, col0, slot0 = node0 + src.n_nodes, col0 + src.dof, slot0 + src.n_points
+        self.fk_desc = d
+
+    def rand_configs(self, num_cfgs):
+        return torch.cat([r.rand_configs(num_cfgs) for r in self.urdf_robots], dim=1)
+
+    def split_configs(self, q):
+        return torch.split(q, [r._n_dofs for r in self.urdf_robots], dim=1)
+
+    def collision(self, q, other=None, show=False):
+        raise NotImplementedError("mesh collision checking (python-fcl in the reference) is outside this package: give the "
+                                  "checkers the ground truth through gt_check_func")
+
+    def compute_forward_kinematics_all_links(self, q, return_collision=False):
+        """One dictionary per robot (urdf_interface.py:857-862)."""
+        q = torch.as_tensor(q)
+        if q.ndim == 1:
+            q = q[None]
+        return [r.compute_forward_kinematics_all_links(qi, return_collision=return_collision)
+                for r, qi in zip(self.urdf_robots, self.split_configs(q))]
+
+    def update_acm(self, link_pairs):
+        self.inter_robot_acm = set(link_pairs) if self.inter_robot_acm is None else self.inter_robot_acm.union(link_pairs)

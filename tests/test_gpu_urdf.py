@@ -143,3 +143,27 @@ def test_fk_checker_from_urdf_path(cuda_device):
     score = checker.collision_score(q).reshape(-1)
     agree = ((score > 0) == (gt(q) > 0)).float().mean()
     assert float(agree) > 0.85
+
+
+def test_multi_robot_feature_map_is_the_concatenation(g, cuda_device):
+    """MultiURDFRobot: the merged joint program equals the robots' own maps side by side (bit for bit), its J^T product the
+    per-robot products, and the per-robot frame dictionaries those of the single robots."""
+    from diffco_b200 import functional as Fn
+    from diffco_b200.collision_interfaces import MultiURDFRobot, URDFRobot
+
+    a = URDFRobot(os.path.join(HERE, "data", URDF["arm7"]), name="arm")
+    b = URDFRobot(os.path.join(HERE, "data", URDF["torso"]), name="torso", base_transform=BASE["torso"])
+    multi = MultiURDFRobot(urdf_robots=[a, b])
+    assert multi.dof == 15 and multi.fk_desc.n_points == 16
+    q = torch.cat([T64(g["arm7_q"]), T64(g["torso_q"])], dim=1).to(cuda_device)
+    x = multi.fkine(q)
+    xa, xb = a.fkine(q[:, :8]), b.fkine(q[:, 8:])
+    assert x.shape == (16, 16, 3) and torch.equal(x, torch.cat([xa, xb], dim=1))
+    gx = torch.randn(16, 16, 3, generator=torch.Generator().manual_seed(8), dtype=torch.float64).to(cuda_device)
+    gq = Fn.fk_vjp(multi.fk_desc, q, gx)
+    want = torch.cat([Fn.fk_vjp(a.fk_desc, q[:, :8].contiguous(), gx[:, :8].contiguous()),
+                      Fn.fk_vjp(b.fk_desc, q[:, 8:].contiguous(), gx[:, 8:].contiguous())], dim=1)
+    assert torch.equal(gq, want)
+    dicts = multi.compute_forward_kinematics_all_links(q.float())
+    assert len(dicts) == 2 and set(dicts[0]) == set(g["arm7_links"]) and set(dicts[1]) == set(g["torso_links"])
+    assert rel(torch.stack([dicts[1][k][0][0] for k in g["torso_links"]], 1), g["torso_trans"]) <= 3e-6

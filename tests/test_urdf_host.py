@@ -68,3 +68,30 @@ def test_rejects_what_the_joint_program_cannot_hold():
                      for i in range(29))
     with pytest.raises(ValueError):
         URDFRobot(f"<robot name='long'>{links}{joints}</robot>")  # 30 bodies > DC_MAX_TREE_NODES
+
+
+def test_multi_robot_merges_the_joint_programs():
+    """MultiURDFRobot (urdf_interface.py:700-870): configurations and feature links concatenated in robot order; the merged
+    descriptor is the robots' programs with node / column / slot indices shifted."""
+    from diffco_b200.collision_interfaces import MultiURDFRobot
+
+    a = URDFRobot(os.path.join(DATA, "torso_two_arms.urdf"), name="t")
+    shift = torch.eye(4)
+    shift[0, 3] = 1.0
+    b = URDFRobot(os.path.join(DATA, "torso_two_arms.urdf"), name="u", base_transform=shift)
+    multi = MultiURDFRobot(urdf_robots=[a, b])
+    assert multi.name == "t_u" and multi.dof == a.dof + b.dof == 14
+    assert multi.unique_position_link_names == [(0, n) for n in a.unique_position_link_names] + [(1, n) for n in b.unique_position_link_names]
+    d = multi.fk_desc
+    assert (d.n_nodes, d.n_points, d.dof) == (18, 16, 14)
+    for k in range(b.fk_desc.n_nodes):
+        m, s = d.tree[a.fk_desc.n_nodes + k], b.fk_desc.tree[k]
+        assert m.parent == (s.parent + 9 if s.parent >= 0 else -1) and m.q_index == (s.q_index + 7 if s.q_index >= 0 else -1)
+        assert m.out_slot == (s.out_slot + 8 if s.out_slot >= 0 else -1) and list(m.rot) == list(s.rot) and list(m.trans) == list(s.trans)
+    q = multi.rand_configs(4)
+    assert q.shape == (4, 14) and [t.shape[1] for t in multi.split_configs(q)] == [7, 7]
+    assert torch.equal(multi.joint_limits, torch.cat([a.joint_limits, b.joint_limits]))
+    with pytest.raises(AssertionError):
+        MultiURDFRobot(urdf_robots=[a, a])
+    with pytest.raises(ValueError):  # 3 x 9 bodies > 24
+        MultiURDFRobot(urdf_paths=[os.path.join(DATA, "torso_two_arms.urdf")] * 3, names=["a", "b", "c"])
