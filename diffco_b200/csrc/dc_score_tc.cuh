@@ -1120,7 +1120,13 @@ __global__ void __launch_bounds__(TcLayoutT<FG>::THREADS, TcLayoutT<FG>::CTAS_PE
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
+#ifndef DC_TC_QREGS
+#define DC_TC_QREGS 104  // 112 would fill the register file exactly (2 x (8 x 32 x 112 + 4 x 32 x 32) = 65536) and was tried
+#endif                   // to stop ptxas rematerialising addresses in the chunk loop: the second CTA's setmaxnreg.inc never
+                         // returns (the launch-time allocation of 80 x 384 leaves no slack) — the kernel hangs.  Do not raise.
+#define DC_TC_STR2(x) #x
+#define DC_TC_STR(x) DC_TC_STR2(x)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " DC_TC_STR(DC_TC_QREGS) ";" ::: "memory");
     // ================= query threads: row = 32 (warp & 3) + lane, column half = warp >> 2 ==========================
     const int row = ((warp & 3) << 5) | lane;
     const int hcol = warp >> 2;
