@@ -1,4 +1,6 @@
-// Fused collision-score kernel, tensor-core form (tcgen05 + TMEM + bulk TMA; RQKernel(p = 2), one class, fp32 I/O, F <= 14).
+// Fused collision-score kernel, tensor-core form (tcgen05 + TMEM + bulk TMA; RQKernel(p = 2), one class, fp32 I/O, F <= 30:
+// operand groups of FG = 16 K slots for F <= 14 — the shapes written out below, two CTAs per SM — or FG = 32 for F <= 30,
+// one CTA per SM; everything is a template on FG).
 //
 //   score[b] = sum_n w_n u_bn^2      g_x[b] = -2 gamma sum_n w_n u_bn^3 (x_b - s_n)      u = 1 / (1 + gamma/2 |x_b - s_n|^2)
 //
