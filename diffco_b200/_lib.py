@@ -21,7 +21,7 @@ DC_MAX_FEATURES = 64
 DC_MAX_TREE_NODES = 24
 DC_MAX_CLASSES = 8
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 DC_F32, DC_F64 = 0, 1
 DC_FK_NONE, DC_FK_PLANAR_CHAIN, DC_FK_SE2_BODY, DC_FK_SE3_BODY, DC_FK_DH_ARMS, DC_FK_SE2_BASE_PLANAR_ARM, DC_FK_JOINT_TREE = range(7)
 DC_JOINT_FIXED, DC_JOINT_REV_X, DC_JOINT_REV_Y, DC_JOINT_REV_Z, DC_JOINT_PRISMATIC = range(5)
@@ -173,6 +173,8 @@ PROTOTYPES = {
     "dc_peer_barrier": (C.c_int, [C.POINTER(PeerTable), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]),
     "dc_score_grad_bcast": (C.c_int, [C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p, C.c_int64,
                                       C.POINTER(PeerTable), C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dc_score_grad_bcast_sync": (C.c_int, [C.POINTER(FkDesc), C.POINTER(KernelDesc), C.POINTER(Supports), C.c_void_p, C.c_int64,
+                                      C.POINTER(PeerTable), C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(PeerTable), C.c_int32, C.c_uint32, C.c_void_p]),
     "dc_traj_step": (C.c_int, [C.POINTER(FkDesc), C.POINTER(TrajParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dc_traj_dense_path": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,

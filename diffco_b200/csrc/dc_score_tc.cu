@@ -110,10 +110,33 @@ static void* device_alias(const void* p) {
   return nullptr;
 }
 
-int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q, int64_t batch,
-                  void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out, int32_t grad_mode,
-                  int num_sms, cudaStream_t stream, const dc_peer_table* bcast, int n_bcast, void* mirror) {
+// device counter of finished CTAs for the in-kernel step barrier (one sync launch at a time per device: PeerExchange
+// issues them on one stream); the kernel leaves it at 0
+__device__ unsigned int g_tc_done_counter = 0;
+extern double g_peer_timeout_s;  // dc_peer.cu (DC_OPT_PEER_TIMEOUT_S)
+
+static int tc_score_grad_sync(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
+                              int64_t batch, void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out,
+                              int32_t grad_mode, int num_sms, cudaStream_t stream, const dc_peer_table* bcast, int n_bcast,
+                              void* mirror, const dc_peer_table* flags, int rank, uint32_t epoch) {
   TcArgs a;
+  a.sync_world = 0;
+  a.flag_mine = nullptr;
+  a.done = nullptr;
+  a.epoch = epoch;
+  a.sync_timeout_cycles = (long long)(g_peer_timeout_s * 2.0e9);
+  for (int k = 0; k < DC_MAX_PEERS; ++k) a.flag_peer[k] = nullptr;
+  if (flags != nullptr) {
+    void* cnt = nullptr;
+    if (cudaGetSymbolAddress(&cnt, g_tc_done_counter) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return DC_ERR_CUDA;
+    }
+    a.done = static_cast<unsigned int*>(cnt);
+    a.sync_world = n_bcast;
+    a.flag_mine = static_cast<const uint32_t*>(flags->ptr[rank]);
+    for (int k = 0; k < n_bcast; ++k) a.flag_peer[k] = static_cast<uint32_t*>(flags->ptr[k]) + rank;
+  }
   a.mirror = static_cast<float*>(mirror);
   a.n_bcast = n_bcast;
   for (int k = 0; k < DC_MAX_PEERS; ++k) a.bcast[k] = (bcast && k < n_bcast) ? static_cast<float*>(bcast->ptr[k]) : nullptr;
@@ -143,6 +166,13 @@ int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_s
   a.tol_pair = (float)g_tc_tol_pair;
   return grad_mode == DC_GRAD_NONE ? launch_score_tc<TC_SCORE>(a, num_sms, stream)
                                    : launch_score_tc<TC_GRAD>(a, num_sms, stream);
+}
+
+int tc_score_grad(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q, int64_t batch,
+                  void* score, int64_t score_ld, void* grad, int64_t grad_ld, const void* grad_out, int32_t grad_mode,
+                  int num_sms, cudaStream_t stream, const dc_peer_table* bcast, int n_bcast, void* mirror) {
+  return tc_score_grad_sync(fk, kernel, sv, q, batch, score, score_ld, grad, grad_ld, grad_out, grad_mode, num_sms, stream, bcast,
+                            n_bcast, mirror, nullptr, 0, 0);
 }
 
 }  // namespace dc
@@ -202,6 +232,31 @@ int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, cons
   float* mine = static_cast<float*>(outs->ptr[0]) + row_offset * rec;  // the kernel adds (mine - outs[0]) to every base
   return tc_score_grad(fk, kernel, sv, qd, batch, mine, rec, grad_mode == DC_GRAD_SUM ? mine + 1 : nullptr, rec, nullptr,
                        grad_mode, num_sms, (cudaStream_t)stream, outs, n_outs, md);
+}
+
+int dc_score_grad_bcast_sync(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
+                             int64_t batch, const dc_peer_table* outs, int32_t n_outs, int64_t row_offset, int32_t grad_mode,
+                             void* mirror, const dc_peer_table* flags, int32_t rank, uint32_t epoch, dc_stream_t stream) {
+  if (!fk || !kernel || !sv || !outs || !flags || n_outs < 1 || n_outs > DC_MAX_PEERS || row_offset < 0 || rank < 0 ||
+      rank >= n_outs)
+    return DC_ERR_INVALID_ARG;
+  if (batch <= 0 || !q || !sv->table) return DC_ERR_INVALID_ARG;  // every rank must launch: an empty shard cannot take part
+  if (grad_mode != DC_GRAD_NONE && grad_mode != DC_GRAD_SUM) return DC_ERR_INVALID_ARG;
+  for (int k = 0; k < n_outs; ++k)
+    if (!outs->ptr[k] || (reinterpret_cast<uintptr_t>(outs->ptr[k]) & 15) != 0 || !flags->ptr[k]) return DC_ERR_INVALID_ARG;
+  if (!takes_tensor_core_kernel(*fk, *kernel, *sv, batch, grad_mode)) return DC_ERR_UNSUPPORTED;
+  int dev = 0, num_sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return DC_ERR_NO_DEVICE;
+  }
+  const void* qd = device_alias(q);
+  void* md = mirror ? device_alias(mirror) : nullptr;
+  if (!qd || (mirror && !md)) return DC_ERR_INVALID_ARG;
+  const int64_t rec = 1 + (grad_mode == DC_GRAD_SUM ? fk->dof : 0);
+  float* mine = static_cast<float*>(outs->ptr[0]) + row_offset * rec;
+  return tc_score_grad_sync(fk, kernel, sv, qd, batch, mine, rec, grad_mode == DC_GRAD_SUM ? mine + 1 : nullptr, rec, nullptr,
+                            grad_mode, num_sms, (cudaStream_t)stream, outs, n_outs, md, flags, rank, epoch);
 }
 
 int dc_set_option(int32_t option, double value) { return tc_set_option(option, value); }

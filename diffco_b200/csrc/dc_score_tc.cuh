@@ -165,6 +165,15 @@ struct TcArgs {
                                // (a mapped pinned host buffer: the end-to-end path of the multi-GPU scorer)
   float err_coef;  // delta(rho) <= err_coef * (|x|^2 + max_chunk |s|^2)
   float tol_pair;  // admissible |w|-relative error of one pair
+  // Step barrier folded into the kernel's tail (dc_score_grad_bcast_sync; sync_world == 0: none).  The last CTA to finish
+  // (counted in *done) publishes `epoch` into this rank's slot of every rank's flag array and waits for every rank's epoch
+  // in its own — what dc_peer_barrier does as a second launch.
+  uint32_t* flag_peer[DC_MAX_PEERS];  // my slot in rank r's flag array
+  const uint32_t* flag_mine;          // my flag array (slot r = rank r's epoch)
+  unsigned int* done;                 // device counter, 0 between launches
+  long long sync_timeout_cycles;
+  uint32_t epoch;
+  int sync_world;
 };
 
 // ---- tcgen05 / TMEM wrappers ---------------------------------------------------------------------------------
@@ -1328,6 +1337,30 @@ __global__ void __launch_bounds__(TcLayoutT<FG>::THREADS, TcLayoutT<FG>::CTAS_PE
       tc_epilogue<MODE, FG>(a, ti, ntile, sc2.lo() + sc2.hi());
     }
     if (tid == TM && a.n_bcast > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // peer stores performed
+    if (a.sync_world > 0 && owner) {
+      // every record this CTA sent (bulk stores of thread TM, per-thread stores of all owners on the unaligned path) is
+      // ordered before the count; the last CTA of the grid then runs the flag exchange for the whole launch
+      __threadfence_system();
+      named_sync(TCB_OWN, TM);
+      if (tid == TM) {
+        const unsigned int prev = atomicAdd(a.done, 1u);
+        if (prev == gridDim.x - 1) {
+          *a.done = 0u;  // for the next launch (stream order)
+          __threadfence_system();
+          for (int r = 0; r < a.sync_world; ++r)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_peer[r]), "r"(a.epoch) : "memory");
+          const long long t_start = clock64();
+          for (int r = 0; r < a.sync_world; ++r) {
+            for (;;) {
+              uint32_t v;
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flag_mine + r) : "memory");
+              if ((int32_t)(v - a.epoch) >= 0) break;
+              if (clock64() - t_start > a.sync_timeout_cycles) __trap();  // a rank that never arrives must not hang the GPU
+            }
+          }
+        }
+      }
+    }
   }
 
   // teardown: the MMA issuer (owner of the TMEM allocation) waits for the query warps; the TMA warps just leave

@@ -149,6 +149,10 @@ class PeerExchange:
                                       device=device) for k in range(2)]
         self.epoch = 0   # barriers so far
         self.steps = 0   # scoring steps so far (selects the buffer)
+        # DIFFCO_B200_PEER_SYNC=1: the step barrier runs in the tail of the scoring kernel (dc_score_grad_bcast_sync, one launch
+        # per step) instead of a second launch.  Measured at 2 GPUs: 0.1111 vs 0.1101 ms per step — the launch gap is not what
+        # the barrier costs (profiles/r03m_barrier_variants.txt) — so two launches stay the default.
+        self.fold_barrier = os.environ.get("DIFFCO_B200_PEER_SYNC", "0") == "1"
 
     def release(self):
         """Collective: every rank stops using the mapped buffers, THEN they are unmapped and freed (a rank must not free
@@ -181,15 +185,24 @@ class PeerExchange:
         b = q_shard.shape[0]
         k = self.steps & 1
         stream = functional._stream_ptr(self.device)
+        mptr = None if mirror is None else mirror.data_ptr()
         with torch.cuda.device(self.device):
-            st = self.lib.dc_score_grad_bcast(C.byref(fk), C.byref(kdesc), C.byref(sv.desc), q_shard.data_ptr(), b,
-                                              C.byref(self.outs[k]), self.world, self.rank * b, DC_GRAD_SUM,
-                                              None if mirror is None else mirror.data_ptr(), stream)
+            if self.fold_barrier:
+                # ONE launch: the last CTA of the grid runs the flag exchange (dc_score_grad_bcast_sync)
+                st = self.lib.dc_score_grad_bcast_sync(C.byref(fk), C.byref(kdesc), C.byref(sv.desc), q_shard.data_ptr(), b,
+                                                       C.byref(self.outs[k]), self.world, self.rank * b, DC_GRAD_SUM, mptr,
+                                                       C.byref(self.flags), self.rank, self.epoch + 1, stream)
+            else:
+                st = self.lib.dc_score_grad_bcast(C.byref(fk), C.byref(kdesc), C.byref(sv.desc), q_shard.data_ptr(), b,
+                                                  C.byref(self.outs[k]), self.world, self.rank * b, DC_GRAD_SUM, mptr, stream)
             if st == -2:  # DC_ERR_UNSUPPORTED
                 return None
             _lib.check(st, "dc_score_grad_bcast")
         self.steps += 1
-        self.barrier()
+        if self.fold_barrier:
+            self.epoch += 1
+        else:
+            self.barrier()
         return self.views[k]
 
     def barrier(self):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 6
+#define DC_ABI_VERSION 7
 
 #define DC_MAX_DOF 16
 #define DC_MAX_LINKS 16
@@ -289,6 +289,13 @@ int dc_peer_open(const dc_peer_handle* handle, void** ptr);
 int dc_peer_close(void* ptr);
 int dc_peer_free(void* ptr);
 int dc_peer_barrier(const dc_peer_table* flags, int32_t rank, int32_t world, uint32_t epoch, dc_stream_t stream);
+/* dc_score_grad_bcast + dc_peer_barrier in ONE launch: the last CTA of the grid to finish publishes `epoch` and waits
+ * for every rank's — the step is complete (this rank's gathered buffer holds every rank's records) when the kernel ends.
+ * Every rank must call it for every step with the same epoch sequence as dc_peer_barrier (the two may be mixed);
+ * one such launch in flight per device. */
+int dc_score_grad_bcast_sync(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
+                             int64_t batch, const dc_peer_table* outs, int32_t n_outs, int64_t row_offset, int32_t grad_mode,
+                             void* mirror, const dc_peer_table* flags, int32_t rank, uint32_t epoch, dc_stream_t stream);
 int dc_score_grad_bcast(const dc_fk_desc* fk, const dc_kernel_desc* kernel, const dc_supports* sv, const void* q,
                         int64_t batch, const dc_peer_table* outs, int32_t n_outs, int64_t row_offset, int32_t grad_mode,
                         void* mirror, dc_stream_t stream);

@@ -11,7 +11,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, ret, rname="planar7", b=4224):
+def _worker(rank, world, port, ret, rname="planar7", b=4224, fold="0"):
     import torch.distributed as dist
 
     from diffco_b200 import DiffCo, _lib
@@ -20,6 +20,7 @@ def _worker(rank, world, port, ret, rname="planar7", b=4224):
     from tests import problems as P
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["DIFFCO_B200_PEER_SYNC"] = fold  # "1": the step barrier in the tail of the scoring kernel (one launch)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.cuda.set_device(0)
@@ -55,10 +56,11 @@ def _worker(rank, world, port, ret, rname="planar7", b=4224):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("rname,b", [("planar7", 4224), ("se2arm", 4099)])
-def test_fused_all_gather_two_ranks_one_device(rname, b, cuda_device):
+@pytest.mark.parametrize("rname,b,fold", [("planar7", 4224, "0"), ("se2arm", 4099, "0"), ("planar7", 4224, "1"), ("se2arm", 4099, "1")])
+def test_fused_all_gather_two_ranks_one_device(rname, b, fold, cuda_device):
     """planar7: 8-float records, 33 full tiles per rank (bulk-TMA peer stores).  se2arm: 7-float records and a ragged shard, so
-    rank 1's block starts at an address that is NOT 16-byte aligned — the per-thread store path must take over."""
+    rank 1's block starts at an address that is NOT 16-byte aligned — the per-thread store path must take over.  fold = "1":
+    dc_score_grad_bcast_sync (the barrier in the kernel's tail) instead of dc_score_grad_bcast + dc_peer_barrier."""
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
@@ -66,7 +68,7 @@ def test_fused_all_gather_two_ranks_one_device(rname, b, cuda_device):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, rname, b)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, rname, b, fold)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
