@@ -1137,7 +1137,11 @@ __global__ void __launch_bounds__(TcLayoutT<FG>::THREADS, TcLayoutT<FG>::CTAS_PE
                          // returns (the launch-time allocation of 80 x 384 leaves no slack) — the kernel hangs.  Do not raise.
 #define DC_TC_STR2(x) #x
 #define DC_TC_STR(x) DC_TC_STR2(x)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 " DC_TC_STR(DC_TC_QREGS) ";" ::: "memory");
+    if constexpr (FG == 16) {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 " DC_TC_STR(DC_TC_QREGS) ";" ::: "memory");
+    } else {  // one CTA per SM: 8 x 32 x 168 + 4 x 32 x 32 = 47 K of the 64 K registers — room to spare, no spills
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
+    }
     // ================= query threads: row = 32 (warp & 3) + lane, column half = warp >> 2 ==========================
     const int row = ((warp & 3) << 5) | lane;
     const int hcol = warp >> 2;

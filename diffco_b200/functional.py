@@ -298,6 +298,8 @@ class _ScoreFunction(torch.autograd.Function):
                 return grad.to(q.dtype), None
             _, jac = ctx.evaluator(q, _lib.DC_GRAD_JAC)
         # mul + sum (not einsum / bmm): both have batching rules, which the vmapped backward needs
+        if jac.shape[-2] == 1:  # one class: (B, 1) * (B, D), a single elementwise kernel
+            return grad_score.to(jac.dtype) * jac[..., 0, :], None
         return (grad_score.to(jac.dtype).unsqueeze(-1) * jac).sum(-2), None
 
 
