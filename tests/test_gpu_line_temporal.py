@@ -117,3 +117,48 @@ def test_training_on_space_time_points(cuda_device):
     assert bool(((sc > 0) == (y > 0)).all())
     Kmat = kfun(X.to(cuda_device), dc.support_points)
     assert rel(sc, (Kmat.cpu() @ dc.gains.reshape(-1).cpu()).numpy()) <= 1e-9
+
+
+@pytest.mark.parametrize("rname", ["baxter", "se2", "urdf_torso"])
+def test_composite_maps_on_other_robots_match_the_oracle(rname, cuda_device):
+    """LineFKKernel / TemporalFKKernel wrap ANY robot's map (DH arms, rigid bodies, URDF trees): fused score + gradient in
+    float64 against the oracle's statement of kernel.py:145-202 on the oracle's own FK of that robot."""
+    from diffco_b200 import DiffCo
+    from diffco_b200 import kernel as K
+    from oracle import diffco_oracle as O
+
+    if rname == "urdf_torso":
+        from diffco_b200.collision_interfaces import URDFRobot
+
+        robot = URDFRobot(os.path.join(os.path.dirname(__file__), "data", "torso_two_arms.urdf"))
+        nodes = P.tree_nodes_from_desc(robot.fk_desc)
+        fk = lambda q: O.fk_joint_tree(q, nodes, robot.fk_desc.n_points)[0]
+    else:
+        robot = P.make_robot(rname)
+        fk = P.oracle_fk(robot)
+    gen = torch.Generator().manual_seed(21)
+    lim = robot.limits.double()
+    draw = lambda n: torch.rand(n, robot.dof, generator=gen, dtype=torch.float64) * (lim[:, 1] - lim[:, 0]) + lim[:, 0]
+    w = torch.randn(40, generator=gen, dtype=torch.float64)
+    # segments [q_a | q_b]
+    S, Q = torch.cat([draw(40), draw(40)], 1), torch.cat([draw(25), draw(25)], 1)
+    Q[3] = S[5]
+    want = lambda q: O.line_fk_kernel(q, S, fk, 10.0) @ w
+    s_ref, g_ref = O.score_and_grad(want, Q)
+    dc = DiffCo(kernel_func=K.LineFKKernel(robot.fkine, K.RQKernel(10.0)))
+    dc.support_points = S.to(cuda_device)
+    dc.support_transformed = dc._shape_features(dc._features(dc.support_points))
+    dc.gains = w.to(cuda_device)
+    s, g = dc.score_and_grad(Q.to(cuda_device))
+    assert rel(s.reshape(-1), s_ref.reshape(-1).numpy()) <= 1e-10 and rel(g, g_ref.numpy()) <= 1e-9
+    # space-time points [q | t]
+    St, Qt = torch.cat([draw(40), torch.rand(40, 1, generator=gen, dtype=torch.float64)], 1), torch.cat(
+        [draw(25), torch.rand(25, 1, generator=gen, dtype=torch.float64)], 1)
+    want_t = lambda q: O.temporal_fk_kernel(q, St, fk, 10.0, 2, 4.0, 1, 0.7) @ w
+    s_ref, g_ref = O.score_and_grad(want_t, Qt)
+    dct = DiffCo(kernel_func=K.TemporalFKKernel(robot.fkine, K.RQKernel(10.0), K.RQKernel(4.0, 1), alpha=0.7))
+    dct.support_points = St.to(cuda_device)
+    dct.support_transformed = dct._shape_features(dct._features(dct.support_points))
+    dct.gains = w.to(cuda_device)
+    s, g = dct.score_and_grad(Qt.to(cuda_device))
+    assert rel(s.reshape(-1), s_ref.reshape(-1).numpy()) <= 1e-10 and rel(g, g_ref.numpy()) <= 1e-9
