@@ -511,6 +511,7 @@ def run_extras(args, torch, dist, lib, dev, rank, world, group, scorer, checker,
     if world == 1:
         cfgs["cfg3"] = bench_cfg3(torch, lib, dev, timed, hbm_peak)
         cfgs["wide_tc"] = bench_wide(torch, lib, dev, timed)
+        cfgs["fp64"] = bench_fp64(torch, lib, dev, timed, S, w, q)
         cfgs["cfg4"] = bench_cfg4(torch, dev)
         cfgs["fit"] = bench_fit(torch, dev)
         # ---- the reference's own ATen code on this GPU (courtesy row: fused vs unfused on identical silicon) --------------
@@ -604,6 +605,29 @@ def bench_wide(torch, lib, dev, timed):
     finally:
         lib.dc_set_option(_lib.DC_OPT_TC_ENABLE, tc_was)
     return out
+
+
+def bench_fp64(torch, lib, dev, timed, S, w, q):
+    """The headline workload in float64 — the dtype the reference's scripts run in (its CPU figure: cpu_baseline.float64):
+    same supports and queries, lane-split kernel (the float64 path is built for the optimisers' small batches; this is its
+    large-batch rate)."""
+    from diffco_b200 import DiffCo, _lib
+    from diffco_b200 import distributed as D
+    from diffco_b200 import kernel as K
+    from diffco_b200 import model as M
+
+    robot = M.RevolutePlanarRobot(1.0, 0.3, dof=DOF)
+    chk = DiffCo(kernel_func=K.RQKernel(GAMMA), transform=robot.fkine)
+    chk.support_points = S.double().to(dev)
+    chk.support_transformed = robot.fkine(chk.support_points)
+    chk.gains = w.double().to(dev)
+    sc = D.ShardedScorer(chk, weights="gains")
+    qd = q.double().to(dev)
+    steps = 5
+    ms, _, _, _ = timed(lambda: sc.local_score_and_grad(qd), steps, 2, sc=None)
+    t = ms * 1e-3 / steps
+    return {"workload": WORKLOAD.replace("fp32", "fp64"), "value": len(q) / t, "unit": UNIT, "ms_per_step": 1e3 * t, "steps": steps,
+            "kernel": _lib.KERNEL_NAMES.get(lib.dc_last_score_kernel(), "?") + " (score_ls_kernel<double>)"}
 
 
 def bench_cfg4(torch, dev):
