@@ -192,3 +192,21 @@ def test_autograd_plumbing_with_a_stub_evaluator():
     (g1,) = torch.autograd.grad(Fn.differentiable_score(q, evaluator).sum(), q, create_graph=True)
     with pytest.raises(RuntimeError):
         g1.sum().backward()
+
+
+def test_integration_md_stub_matches_the_binding():
+    """The ctypes stub INTEGRATION.md shows a reference maintainer is executable and its structures have the sizes of the
+    real binding (diffco_b200/_lib.py), which the layout test above pins to the header."""
+    import ctypes
+    import re
+
+    from diffco_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    stub = re.findall(r"```python\n(.*?)```", text, re.S)[0]
+    stub = stub.replace('C.CDLL("libdiffco_b200.so")', f'C.CDLL("{_lib.LIB_PATH}")')
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    for name in ("DhArm", "TreeNode", "FkDesc", "KernelDesc", "Supports"):
+        assert ctypes.sizeof(ns[name]) == ctypes.sizeof(getattr(_lib, name)), name
